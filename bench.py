@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+# -*- coding: utf-8 -*-
+"""
+bench.py -- headline benchmark: grid-points/s of the 2D optimized-convolution Barnes
+interpolation (n=4) on the paper grid, batched independent fields (BASELINE.json configs[4]
+shape: 2400x1200, step 1/32, sigma 1.0, N=50 000 samples per field).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--fields F] [--impl reference]
+
+One process per GPU (torchrun sets RANK/LOCAL_RANK/WORLD_SIZE for N>1).  A step = one pass of
+the hot path (centre -> inject -> x sweep -> y sweep + mask/divide/cast) over a batch of F fields
+per GPU.  `value` is measured with the samples resident in HBM (CUDA events, max over ranks);
+`e2e` goes through the HOST-buffer C-ABI call (pinned host memory; H2D of the samples and D2H
+of the float32 fields inside the timed region).  Per-kernel times for the roofline come from
+CUDA events recorded by the library on the launching stream during the same timed steps.
+
+`--impl reference` times the CPU implementation of the same path (the oracle port of the
+reference's Numba code, one field per host thread) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'fast-barnes-py_b200'))
+
+METRIC = 'grid-points/s for 2D optimized_convolution n=4'
+UNIT = 'grid-points/s'
+SIZE = (2400, 1200)
+STEP = 1.0 / 32
+X0 = np.asarray([-26.0 + STEP, 34.5])
+SIGMA = 1.0
+NUM_ITER = 4
+N_PER_FIELD = 50000
+POINTS_PER_FIELD = SIZE[0] * SIZE[1]
+# algorithmic bytes per grid point, fp64 state, two fields (SURVEY.md section 8d / BASELINE.md section 4)
+BYTES_ZERO = 16      # zero-fill of vg, wg
+BYTES_SWEEP_X = 32   # non-final fused sweep: 2 x 8 B read + 2 x 8 B write
+BYTES_SWEEP_Y = 20   # final fused sweep: 2 x 8 B read + 4 B float32 write
+BYTES_TOTAL_2D = 68
+
+
+def make_fields(first_field, nfields):
+    """ synthetic samples of fields [first_field, first_field+nfields): SURVEY.md section 8d, config C5 """
+    pts = np.empty((nfields, N_PER_FIELD, 2))
+    val = np.empty((nfields, N_PER_FIELD))
+    for i in range(nfields):
+        rng = np.random.default_rng(2000 + first_field + i)
+        pts[i] = X0 + rng.uniform(0, 1, (N_PER_FIELD, 2)) * np.asarray([(SIZE[0] - 1) / 32, (SIZE[1] - 1) / 32])
+        val[i] = rng.normal(1000, 10, N_PER_FIELD)
+    return pts, val
+
+
+def config_dict(fields_per_gpu, n_gpus):
+    return {'workload': '2D optimized_convolution, %dx%d grid, step 1/32, sigma 1.0, num_iter 4, batched fields, '
+                        'N=%d samples/field (BASELINE configs[4] shape; configs[0] grid)' % (SIZE[0], SIZE[1], N_PER_FIELD),
+            'fields_per_gpu_per_step': fields_per_gpu, 'fields_per_step': fields_per_gpu * n_gpus,
+            'grid': list(SIZE), 'samples_per_field': N_PER_FIELD, 'parallelism': 'fields sharded, no collective',
+            'cache': 'working set per step (%.1f GB fp64 state) exceeds L2; no flush needed'
+                     % (fields_per_gpu * POINTS_PER_FIELD * 32 / 1e9)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference, one field per thread
+
+def cpu_fields_per_second(nfields, nthreads, repeats=1):
+    from oracle import oracle as orc
+    from concurrent.futures import ThreadPoolExecutor
+    pts, val = make_fields(0, nfields)
+    orc.lib()
+
+    def one(i):
+        return orc.barnes(pts[i], val[i], SIGMA, X0, STEP, SIZE, num_iter=NUM_ITER, nthreads=1)
+
+    one(0)   # warm-up (page faults, library load)
+    best = None
+    with ThreadPoolExecutor(max_workers=nthreads) as ex:
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            list(ex.map(one, range(nfields)))
+            dt = time.perf_counter() - t0
+            best = dt if best is None or dt < best else best
+    return nfields / best, best
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    nfields = max(cores, 8)
+    from oracle import oracle as orc
+    from concurrent.futures import ThreadPoolExecutor
+    pts, val = make_fields(0, nfields)
+    orc.lib()
+
+    def one(i):
+        return orc.barnes(pts[i], val[i], SIGMA, X0, STEP, SIZE, num_iter=NUM_ITER, nthreads=1)
+
+    times = []
+    with ThreadPoolExecutor(max_workers=cores) as ex:
+        for s in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            list(ex.map(one, range(nfields)))
+            dt = time.perf_counter() - t0
+            if s >= args.warmup:
+                times.append(dt)
+    total = sum(times)
+    value = nfields * POINTS_PER_FIELD * len(times) / total
+    sample = '%d fields per step (one per host thread) of the same 2400x1200 / N=50000 workload' % nfields
+    line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * total / len(times),
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': config_dict(nfields, 1),
+            'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
+            'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+
+class ClockSampler:
+    QUERY = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+             'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+             'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.gpu_index = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu_index), '--query-gpu=' + self.QUERY,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t_begin, t_end):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smmax, reasons = [], None, set()
+        for (t, row) in self.rows:
+            f = [x.strip() for x in row.split(',')]
+            if len(f) < 9:
+                continue
+            try:
+                clk = float(f[1])
+                smmax = float(f[2])
+            except ValueError:
+                continue
+            if t_begin - 0.05 <= t <= t_end + 0.05:
+                sm.append(clk)
+                for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[5:9]):
+                    if v.lower().startswith('active'):
+                        reasons.add(name)
+        if not sm:   # timed region shorter than the sampling period: fall back to all samples
+            for (t, row) in self.rows:
+                f = [x.strip() for x in row.split(',')]
+                try:
+                    sm.append(float(f[1]))
+                except (ValueError, IndexError):
+                    pass
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': smmax, 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+
+def run_gpu(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    from fastbarnes import interpolation as fbi
+    from fastbarnes import _lib
+
+    torch.cuda.set_device(local_rank)
+    _lib.check(_lib.lib().fb_set_device(local_rank))
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    F = args.fields
+    L = _lib.lib()
+
+    # ---- device-resident arm ---------------------------------------------------------------------
+    pts_h, val_h = make_fields(rank * F, F)
+    pin_pts = torch.from_numpy(pts_h.reshape(F * N_PER_FIELD, 2)).pin_memory()
+    pin_val = torch.from_numpy(val_h.reshape(F * N_PER_FIELD)).pin_memory()
+    d_pts = pin_pts.to(dev, non_blocking=True)
+    d_val = pin_val.to(dev, non_blocking=True)
+    plan = fbi.BarnesDevice(2, SIGMA, X0, STEP, SIZE, nfields=F, nsamples=F * N_PER_FIELD, num_iter=NUM_ITER, device=dev)
+    torch.cuda.synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        plan(d_pts, d_val)
+    barrier()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.25)
+    L.fb_set_profiling(1)
+    seg = np.zeros(5)
+    seg_ms = np.zeros(5)
+    nl = np.zeros(1, dtype=np.int64)
+    launches0 = L.fb_kernel_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_begin = time.perf_counter()
+    ev0.record()
+    for _ in range(args.steps):
+        plan(d_pts, d_val)
+    ev1.record()
+    barrier()
+    t_end = time.perf_counter()
+    ms_total = ev0.elapsed_time(ev1)
+    launches = L.fb_kernel_launch_count() - launches0
+    # per-kernel durations: re-run the timed count with the library's per-stage events read back
+    # after every step (reading them forces a sync, so this is a separate loop from `value`)
+    for _ in range(args.steps):
+        plan(d_pts, d_val)
+        _lib.check(L.fb_last_profile(seg.ctypes.data_as(_lib.c_double_p), 5, nl.ctypes.data_as(_lib.c_i64_p)))
+        seg_ms += seg
+    seg_ms /= args.steps
+    L.fb_set_profiling(0)
+    clocks = sampler.stop(t_begin, t_end)
+
+    # ---- end-to-end arm: host buffers through the C ABI -----------------------------------------------
+    out_pin = torch.empty((F,) + SIZE[::-1], dtype=torch.float32).pin_memory()
+    prob = plan.prob
+    h2d = pin_pts.numel() * 8 + pin_val.numel() * 8
+    d2h = out_pin.numel() * 4
+
+    def e2e_step():
+        _lib.check(L.fb_barnes_host(prob, F * N_PER_FIELD, None, pin_pts.data_ptr(), pin_val.data_ptr(),
+                                    out_pin.data_ptr(), None))
+
+    for _ in range(max(1, min(args.warmup, 3))):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(1, min(args.steps, 10))
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+
+    # ---- reduce over ranks (max time) ------------------------------------------------------------------
+    t = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, e2e_ms = float(t[0]), float(t[1])
+    if rank == 0:
+        pts_per_step = F * POINTS_PER_FIELD * world
+        value = pts_per_step * args.steps / (ms_total * 1e-3)
+        e2e_value = pts_per_step * e2e_steps / (e2e_ms * 1e-3)
+        peaks = {}
+        try:
+            with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+                peaks = json.load(f)
+        except Exception:
+            pass
+        peak = float(peaks.get('hbm_gbs', 6650.0))
+        peak_src = 'measured (MEASURED_PEAKS.json)' if 'hbm_gbs' in peaks else 'fallback (B200_PROFILING.md)'
+        pts_launch = F * POINTS_PER_FIELD
+        gx = BYTES_SWEEP_X * pts_launch / (seg_ms[2] * 1e-3) / 1e9 if seg_ms[2] > 0 else 0.0
+        gy = BYTES_SWEEP_Y * pts_launch / (seg_ms[3] * 1e-3) / 1e9 if seg_ms[3] > 0 else 0.0
+        dominant_is_x = seg_ms[2] >= seg_ms[3]
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as f:
+                tj = json.load(f)
+            traffic = tj.get('sweep_x_bytes_per_launch' if dominant_is_x else 'sweep_y_bytes_per_launch')
+        except Exception:
+            pass
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f64', 'data': 'synthetic', 'config': config_dict(F, world),
+            'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d * world, 'd2h_bytes_per_step': d2h * world,
+                    'ms_per_step': e2e_ms / e2e_steps, 'steps': e2e_steps,
+                    'api': 'fb_barnes_host (C ABI, pinned host buffers, H2D + kernels + D2H inside)'},
+            'gpu_launches': int(launches),
+            'roofline': {
+                'bound': 'hbm',
+                'kernel': 'fb_sweep_kernel<4,1> (x sweep, 4 fused passes, transposing)' if dominant_is_x
+                          else 'fb_sweep_kernel<4,2> (y sweep, 4 fused passes + mask/divide/cast)',
+                'achieved': gx if dominant_is_x else gy, 'peak': peak, 'unit': 'GB/s',
+                'frac': (gx if dominant_is_x else gy) / peak, 'traffic': traffic, 'peak_source': peak_src,
+                'algorithmic_bytes_per_point': BYTES_SWEEP_X if dominant_is_x else BYTES_SWEEP_Y,
+                'points_per_launch': pts_launch,
+                'ms_per_launch': float(seg_ms[2] if dominant_is_x else seg_ms[3]),
+                'other_kernels': {'sweep_x_GBps': gx, 'sweep_y_GBps': gy, 'ms_zero_fill': float(seg_ms[0]),
+                                  'ms_minmax_inject': float(seg_ms[1]), 'ms_sweep_x': float(seg_ms[2]),
+                                  'ms_sweep_y': float(seg_ms[3])},
+                'whole_step': {'algorithmic_bytes_per_point': BYTES_TOTAL_2D,
+                               'achieved_GBps': BYTES_TOTAL_2D * pts_launch * args.steps / (ms_total * 1e-3) / 1e9 / 1.0,
+                               'frac_of_peak': BYTES_TOTAL_2D * pts_launch * args.steps / (ms_total * 1e-3) / 1e9 / peak},
+            },
+            'clocks': clocks,
+        }
+        if world == 1 and not args.no_cpu:
+            cores = os.cpu_count() or 1
+            nf = max(cores, 8) * 2
+            fps, secs = cpu_fields_per_second(nf, cores)
+            line['cpu_baseline'] = {'value': fps * POINTS_PER_FIELD, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                                    'sample': '%d fields of the same workload, one field per host thread, %.1f s wall'
+                                              % (nf, secs)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--fields', type=int, default=64, help='fields per GPU per step')
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    if args.impl == 'reference':
+        run_reference(args, rank, world)
+        return
+    if world == 1 and args.gpus > 1:
+        # not launched under torchrun: re-launch one process per GPU
+        cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', str(args.gpus),
+               '--master-addr', '127.0.0.1', '--master-port', str(29500 + os.getpid() % 1000), os.path.abspath(__file__),
+               '--gpus', str(args.gpus), '--steps', str(args.steps), '--warmup', str(args.warmup),
+               '--fields', str(args.fields)]
+        sys.exit(subprocess.call(cmd))
+    run_gpu(args, rank, local_rank, world)
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,934 @@
+// fb_api.cu -- C ABI (include/fastbarnes_b200.h) over the sm_100a kernels in fb_kernels.cuh.
+//
+// Host-side responsibilities: kernel parameters (T, alpha, conv_scale_factor) in the exact
+// arithmetic of the reference, workspace carving, the launch plan of the sweeps (how many of
+// the n passes are fused per launch given the on-chip ring storage), and the HOST-buffer
+// convenience entry points (device arena + H2D/D2H).  There is no CPU compute path: every
+// entry point that computes fails with FB_ECUDA when no device is present.
+#include "../../include/fastbarnes_b200.h"
+#include "fb_kernels.cuh"
+
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#define FB_EXPORT extern "C" __attribute__((visibility("default")))
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<long long> g_launches{0};
+std::atomic<int> g_profiling{0};
+
+int fail(int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                         \
+    do {                                                                                       \
+        cudaError_t e_ = (expr);                                                               \
+        if (e_ != cudaSuccess)                                                                 \
+            return fail(FB_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+#define LAUNCH_CHECK()                                                                         \
+    do {                                                                                       \
+        g_launches.fetch_add(1, std::memory_order_relaxed);                                   \
+        cudaError_t e_ = cudaGetLastError();                                                   \
+        if (e_ != cudaSuccess)                                                                 \
+            return fail(FB_ECUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
+
+// ---- profiling (CUDA events on the launching stream) -----------------------------------------
+// segment i lies between event i and event i+1:
+//   0 zero-fill + init   1 min/max + injection   2..4 axis sweeps (x, y, z as far as present)
+constexpr int kProfSegments = 5;
+struct Profile {
+    cudaEvent_t ev[kProfSegments + 1] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    int marked = 0;          // events recorded in the last call
+    bool armed = false;
+    long long launches_begin = 0, launches_end = 0;
+};
+thread_local Profile g_prof;
+
+int prof_mark(int i, cudaStream_t st)
+{
+    if (!g_profiling.load()) return FB_OK;
+    if (!g_prof.ev[i]) CUDA_TRY(cudaEventCreate(&g_prof.ev[i]));
+    CUDA_TRY(cudaEventRecord(g_prof.ev[i], st));
+    if (i + 1 > g_prof.marked) g_prof.marked = i + 1;
+    return FB_OK;
+}
+
+// ---- kernel parameters -------------------------------------------------------------------------
+// `float64 ** int` as Numba lowers it (numba/cpython/numbers.py, int_power_impl):
+// square-and-multiply, not libm pow.
+double int_power(double a, long long b)
+{
+    double r = 1.0;
+    bool invert = false;
+    long long e = b;
+    if (b < 0) { invert = true; e = -b; }
+    if (e > 0x10000) return std::pow(a, (double)b);
+    while (e != 0) {
+        if (e & 1) r *= a;
+        e >>= 1;
+        a *= a;
+    }
+    return invert ? 1.0 / r : r;
+}
+
+struct AxisParams { int T; double alpha; };
+
+// ---- sweeps ------------------------------------------------------------------------------------
+constexpr size_t kSmemLimit = 227 * 1024 - 1024;   // opt-in dynamic smem per CTA, minus slack
+
+size_t sweep_smem_bytes(int npass, int mode, int D)
+{
+    const int nr = npass - 1;
+    size_t b = (size_t)nr * D * 32 * sizeof(double);
+    if (mode == 1) b += (size_t)FB_TILE_K * FB_TILE_PITCH * sizeof(double);
+    return b;
+}
+
+template <int NPASS, int MODE>
+int launch_sweep_t(const FbSweep &p, size_t smem, cudaStream_t st)
+{
+    static thread_local size_t configured[16] = {0};   // per device would be more exact; attribute is sticky per function
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (smem > 48 * 1024 && configured[dev & 15] < smem) {
+        CUDA_TRY(cudaFuncSetAttribute(fb_sweep_kernel<NPASS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)kSmemLimit));
+        CUDA_TRY(cudaFuncSetAttribute(fb_sweep_kernel<NPASS, MODE>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                      cudaSharedmemCarveoutMaxShared));
+        configured[dev & 15] = kSmemLimit;
+    }
+    const long long nwarps = p.n_outer * p.n_groups;
+    if (nwarps <= 0) return FB_OK;
+    if (nwarps > 2147483647LL) return fail(FB_EINVAL, "too many grid lines for one launch: %lld", nwarps);
+    fb_sweep_kernel<NPASS, MODE><<<(unsigned)nwarps, 32, smem, st>>>(p);
+    LAUNCH_CHECK();
+    return FB_OK;
+}
+
+template <int MODE>
+int launch_sweep_m(int npass, const FbSweep &p, size_t smem, cudaStream_t st)
+{
+    switch (npass) {
+    case 1: return launch_sweep_t<1, MODE>(p, smem, st);
+    case 2: return launch_sweep_t<2, MODE>(p, smem, st);
+    case 3: return launch_sweep_t<3, MODE>(p, smem, st);
+    case 4: return launch_sweep_t<4, MODE>(p, smem, st);
+    case 5: return launch_sweep_t<5, MODE>(p, smem, st);
+    case 6: return launch_sweep_t<6, MODE>(p, smem, st);
+    }
+    return fail(FB_EINVAL, "unsupported number of fused passes: %d", npass);
+}
+
+// A pair of fp64 grids (value field, weight field) in device memory.
+struct Pair { double *v, *w; };
+
+// One axis sweep of `num_iter` passes over the grids in `cur`.
+//   mode 0: same layout.    mode 1: transposed output.    mode 2: finalised float32 output.
+// The passes are fused into as few launches as the per-warp ring storage allows (a launch fusing
+// f passes keeps f-1 rings of 2T+2 elements per line in shared memory; f = 1 needs none, so very
+// wide kernels degrade to one launch per pass).  Launches with f >= 2 that keep the layout run in
+// place; single-pass launches and the transposing launch write to `spare`, after which the roles
+// of the two pairs swap.  On return `cur` holds the result (modes 0 and 1).
+int run_sweep(int mode, int num_iter, AxisParams ax, Pair &cur, Pair &spare, float *out32, double *out64,
+              const unsigned long long *mm, double csf, long long n_outer, long long L, long long n_inner,
+              bool has_w, cudaStream_t st)
+{
+    FbSweep p{};
+    p.n_outer = n_outer;
+    p.L = L;
+    p.n_inner = n_inner;
+    p.n_groups = (n_inner + 15) / 16;
+    p.T = ax.T;
+    p.D = 2 * ax.T + 2;
+    p.has_w = has_w ? 1 : 0;
+    p.alpha = ax.alpha;
+    p.csf = csf;
+    p.mm = mm;
+    p.out32 = out32;
+    p.out64 = out64;
+    if (L > 2147483647LL - 8 * (long long)(ax.T + 1) - 64) return fail(FB_EINVAL, "line too long: %lld", L);
+
+    // largest number of passes one launch can fuse
+    int fmax = 1;
+    for (int f = 2; f <= FB_MAX_FUSED_PASSES; ++f)
+        if (sweep_smem_bytes(f, mode, p.D) <= kSmemLimit) fmax = f;
+    const int nlaunch = (num_iter + fmax - 1) / fmax;
+    int remaining = num_iter;
+    for (int l = 0; l < nlaunch; ++l) {
+        const int np = (remaining + (nlaunch - l) - 1) / (nlaunch - l);
+        remaining -= np;
+        const bool last = (l == nlaunch - 1);
+        const int m = last ? mode : 0;
+        const bool in_place = (m == 0 && np >= 2);
+        p.in_v = cur.v;
+        p.in_w = cur.w;
+        if (m == 2) {
+            p.out_v = p.out_w = nullptr;
+        } else if (in_place) {
+            p.out_v = cur.v;
+            p.out_w = cur.w;
+        } else {
+            if (!spare.v || (has_w && !spare.w)) return fail(FB_EINVAL, "internal: sweep needs a spare buffer pair");
+            p.out_v = spare.v;
+            p.out_w = spare.w;
+        }
+        const size_t smem = sweep_smem_bytes(np, m, p.D);
+        if (smem > kSmemLimit) return fail(FB_EKERNEL, "ring storage does not fit: T=%d passes=%d", ax.T, np);
+        int rc = FB_OK;
+        if (m == 0) rc = launch_sweep_m<0>(np, p, smem, st);
+        else if (m == 1) rc = launch_sweep_m<1>(np, p, smem, st);
+        else rc = launch_sweep_m<2>(np, p, smem, st);
+        if (rc != FB_OK) return rc;
+        if (m != 2 && !in_place) { Pair t = cur; cur = spare; spare = t; }
+    }
+    return FB_OK;
+}
+
+// ---- problem validation / derived parameters -----------------------------------------------------
+struct Derived {
+    AxisParams ax[3];
+    int32_t ks[3];
+    double csf;
+    long long W, H, Dz, total;
+};
+
+int derive(const fb_problem *pr, Derived &d)
+{
+    if (!pr) return fail(FB_EINVAL, "null problem");
+    if (pr->dim < 1 || pr->dim > 3) return fail(FB_EINVAL, "dim must be 1, 2 or 3: %d", pr->dim);
+    if (pr->num_iter < 1) return fail(FB_EINVAL, "num_iter must be >= 1: %d", pr->num_iter);
+    if (pr->nfields < 1 || pr->nfields > 65535) return fail(FB_EINVAL, "nfields must be in [1, 65535]: %lld", (long long)pr->nfields);
+    if (pr->method != FB_METHOD_OPTIMIZED_CONVOLUTION && pr->method != FB_METHOD_CONVOLUTION)
+        return fail(FB_EINVAL, "unknown method id: %d", pr->method);
+    d.W = pr->size[0];
+    d.H = pr->dim > 1 ? pr->size[1] : 1;
+    d.Dz = pr->dim > 2 ? pr->size[2] : 1;
+    if (d.W < 1 || d.H < 1 || d.Dz < 1) return fail(FB_EINVAL, "grid size must be positive");
+    d.total = d.W * d.H * d.Dz;
+    double tv[3] = {0, 0, 0};
+    for (int m = 0; m < pr->dim; ++m) {
+        int T;
+        if (pr->method == FB_METHOD_CONVOLUTION) {
+            T = fb_half_kernel_size(pr->sigma[m], pr->step[m], pr->num_iter);
+            tv[m] = 0.0;
+        } else {
+            T = fb_half_kernel_size_opt(pr->sigma[m], pr->step[m], pr->num_iter);
+            tv[m] = fb_tail_value(pr->sigma[m], pr->step[m], pr->num_iter);
+        }
+        if (T < 0) return fail(FB_EINVAL, "negative half kernel size on axis %d", m);
+        d.ax[m].T = T;
+        d.ax[m].alpha = tv[m];
+        d.ks[m] = 2 * T + 1;
+    }
+    d.csf = fb_conv_scale_factor(pr->dim, d.ks, tv, pr->sigma, pr->step, pr->num_iter, pr->max_dist_weight);
+    return FB_OK;
+}
+
+// ---- workspace -----------------------------------------------------------------------------------
+struct Workspace {
+    double *vA, *wA, *vB, *wB;
+    unsigned long long *mm, *counters;
+    long long *offsets;
+    unsigned char *first_mask;
+    int *rec_k;
+    double *rec_w, *rec_wv;
+    long long *seg_node;
+    unsigned int *seg_base, *seg_n;
+    size_t bytes;
+};
+
+// carve (base may be nullptr to only compute the size)
+void carve(Workspace &w, char *base, const fb_problem *pr, long long total, long long nsamples)
+{
+    size_t off = 0;
+    auto take = [&](size_t n) { char *p = base ? base + off : nullptr; off += align_up(n); return p; };
+    const size_t g = (size_t)pr->nfields * (size_t)total * sizeof(double);
+    const size_t R = (size_t)nsamples << pr->dim;
+    w.vA = (double *)take(g);
+    w.wA = (double *)take(g);
+    w.vB = (double *)take(g);
+    w.wB = (double *)take(g);
+    w.mm = (unsigned long long *)take((size_t)pr->nfields * FB_MM_STRIDE * 8);
+    w.counters = (unsigned long long *)take(4 * 8);
+    w.offsets = (long long *)take((size_t)(pr->nfields + 1) * 8);
+    w.first_mask = (unsigned char *)take((size_t)nsamples + 1);
+    w.rec_k = (int *)take(R * 4 + 4);
+    w.rec_w = (double *)take(R * 8 + 8);
+    w.rec_wv = (double *)take(R * 8 + 8);
+    w.seg_node = (long long *)take(R * 8 + 8);
+    w.seg_base = (unsigned int *)take(R * 4 + 4);
+    w.seg_n = (unsigned int *)take(R * 4 + 4);
+    w.bytes = off;
+}
+
+// ---- the pipeline: centre -> inject -> sweeps (+ finalize) -----------------------------------------
+int check_offsets(const fb_problem *pr, long long nsamples, const int64_t *off, long long &max_n)
+{
+    if (nsamples < 0) return fail(FB_EINVAL, "negative sample count");
+    if (!off) {
+        if (nsamples % pr->nfields) return fail(FB_EINVAL, "nsamples (%lld) is not a multiple of nfields (%lld) and no sample_offsets given", nsamples, (long long)pr->nfields);
+        max_n = nsamples / pr->nfields;
+        return FB_OK;
+    }
+    max_n = 0;
+    if (off[0] != 0 || off[pr->nfields] != nsamples) return fail(FB_EINVAL, "sample_offsets must start at 0 and end at nsamples");
+    for (long long b = 0; b < pr->nfields; ++b) {
+        long long n = off[b + 1] - off[b];
+        if (n < 0) return fail(FB_EINVAL, "sample_offsets must be non-decreasing");
+        if (n > max_n) max_n = n;
+    }
+    return FB_OK;
+}
+
+int run_inject(const fb_problem *pr, const Derived &d, long long nsamples, const int64_t *h_offsets,
+               const double *d_pts, const double *d_val, Workspace &w, cudaStream_t st)
+{
+    long long max_n = 0;
+    int rc = check_offsets(pr, nsamples, h_offsets, max_n);
+    if (rc != FB_OK) return rc;
+    if (max_n > 2147483647LL) return fail(FB_EINVAL, "too many samples in one field");
+    if ((nsamples << pr->dim) > 4294967295LL) return fail(FB_EINVAL, "too many sample records");
+    const size_t g = (size_t)pr->nfields * (size_t)d.total * sizeof(double);
+    CUDA_TRY(cudaMemsetAsync(w.vA, 0, g, st));
+    CUDA_TRY(cudaMemsetAsync(w.wA, 0, g, st));
+    fb_init_kernel<<<(unsigned)((pr->nfields + 255) / 256), 256, 0, st>>>(w.mm, pr->nfields, w.counters);
+    LAUNCH_CHECK();
+    {
+        int prc = prof_mark(1, st);
+        if (prc != FB_OK) return prc;
+    }
+    FbSamples s{};
+    s.pts = d_pts;
+    s.val = d_val;
+    if (h_offsets) {
+        CUDA_TRY(cudaMemcpyAsync(w.offsets, h_offsets, (size_t)(pr->nfields + 1) * 8, cudaMemcpyHostToDevice, st));
+        s.offsets = w.offsets;
+        s.n_uniform = 0;
+    } else {
+        s.offsets = nullptr;
+        s.n_uniform = max_n;
+    }
+    if (max_n == 0) return FB_OK;
+    FbGrid gr{};
+    gr.dim = pr->dim;
+    gr.W = d.W; gr.H = d.H; gr.Dz = d.Dz; gr.total = d.total;
+    for (int m = 0; m < 3; ++m) { gr.x0[m] = pr->x0[m]; gr.step[m] = pr->step[m]; }
+
+    const unsigned nf = (unsigned)pr->nfields;
+    long long mmb = (max_n + 256 * 8 - 1) / (256 * 8);
+    if (mmb > 1024) mmb = 1024;
+    fb_minmax_kernel<<<dim3((unsigned)mmb, nf), 256, 0, st>>>(s, w.mm);
+    LAUNCH_CHECK();
+    const dim3 sg((unsigned)((max_n + 255) / 256), nf);
+    fb_inject_count_kernel<<<sg, 256, 0, st>>>(s, gr, w.vA, w.wA, w.first_mask);
+    LAUNCH_CHECK();
+    fb_inject_alloc_kernel<<<sg, 256, 0, st>>>(s, gr, w.vA, w.wA, w.first_mask, w.counters, w.seg_node, w.seg_base, w.seg_n);
+    LAUNCH_CHECK();
+    fb_inject_place_kernel<<<sg, 256, 0, st>>>(s, gr, w.vA, w.wA, w.mm, w.rec_k, w.rec_w, w.rec_wv);
+    LAUNCH_CHECK();
+    const long long R = nsamples << pr->dim;
+    long long rblocks = (R + 127) / 128;
+    if (rblocks > 148 * 16) rblocks = 148 * 16;
+    fb_inject_reduce_kernel<<<(unsigned)rblocks, 128, 0, st>>>(w.counters, w.seg_node, w.seg_base, w.seg_n,
+                                                                        w.rec_k, w.rec_w, w.rec_wv, w.vA, w.wA);
+    LAUNCH_CHECK();
+    return FB_OK;
+}
+
+int run_sweeps(const fb_problem *pr, const Derived &d, Workspace &w, float *d_out, double *d_out64, cudaStream_t st)
+{
+    const long long nf = pr->nfields;
+    const int n = pr->num_iter;
+    Pair cur{w.vA, w.wA}, spare{w.vB, w.wB};
+    int rc;
+    if (pr->dim == 1) {
+        rc = run_sweep(2, n, d.ax[0], cur, spare, d_out, d_out64, w.mm, d.csf, nf, d.W, 1, true, st);
+        if (rc != FB_OK) return rc;
+        return prof_mark(3, st);
+    }
+    // x sweep: A layout [..][x][y] -> natural layout [..][y][x]
+    rc = run_sweep(1, n, d.ax[0], cur, spare, nullptr, nullptr, w.mm, d.csf, nf * d.Dz, d.W, d.H, true, st);
+    if (rc != FB_OK) return rc;
+    if ((rc = prof_mark(3, st)) != FB_OK) return rc;
+    if (pr->dim == 2) {
+        rc = run_sweep(2, n, d.ax[1], cur, spare, d_out, d_out64, w.mm, d.csf, nf, d.H, d.W, true, st);
+        if (rc != FB_OK) return rc;
+        return prof_mark(4, st);
+    }
+    rc = run_sweep(0, n, d.ax[1], cur, spare, nullptr, nullptr, w.mm, d.csf, nf * d.Dz, d.H, d.W, true, st);
+    if (rc != FB_OK) return rc;
+    if ((rc = prof_mark(4, st)) != FB_OK) return rc;
+    rc = run_sweep(2, n, d.ax[2], cur, spare, d_out, d_out64, w.mm, d.csf, nf, d.Dz, d.H * d.W, true, st);
+    if (rc != FB_OK) return rc;
+    return prof_mark(5, st);
+}
+
+int check_kernel_vs_grid(const fb_problem *pr, const Derived &d)
+{
+    // interpolation.py:171-175 / :180-184: the rectangular kernel must be smaller than the grid
+    for (int m = 0; m < pr->dim; ++m)
+        if (d.ks[m] >= pr->size[m])
+            return fail(FB_EKERNEL, "resulting rectangular kernel size should be smaller w.r.t. specified grid: axis %d kernel %d grid %lld",
+                        m, d.ks[m], (long long)pr->size[m]);
+    return FB_OK;
+}
+
+int pipeline(const fb_problem *pr, long long nsamples, const int64_t *h_offsets, const double *d_pts,
+             const double *d_val, float *d_out, double *d_out64, void *d_ws, long long ws_bytes,
+             cudaStream_t st, bool enforce_kernel_check)
+{
+    Derived d;
+    int rc = derive(pr, d);
+    if (rc != FB_OK) return rc;
+    if (enforce_kernel_check) {
+        rc = check_kernel_vs_grid(pr, d);
+        if (rc != FB_OK) return rc;
+    }
+    Workspace w;
+    carve(w, (char *)d_ws, pr, d.total, nsamples);
+    if ((long long)w.bytes > ws_bytes) return fail(FB_ENOMEM, "workspace too small: need %zu bytes, got %lld", w.bytes, ws_bytes);
+    g_prof.launches_begin = g_launches.load();
+    g_prof.marked = 0;
+    if ((rc = prof_mark(0, st)) != FB_OK) return rc;
+    rc = run_inject(pr, d, nsamples, h_offsets, d_pts, d_val, w, st);
+    if (rc != FB_OK) return rc;
+    if ((rc = prof_mark(2, st)) != FB_OK) return rc;
+    rc = run_sweeps(pr, d, w, d_out, d_out64, st);
+    if (rc != FB_OK) return rc;
+    g_prof.launches_end = g_launches.load();
+    g_prof.armed = g_profiling.load() != 0;
+    return FB_OK;
+}
+
+// ---- device arena for the *_host entry points ------------------------------------------------------
+struct Arena {
+    void *ptr = nullptr;
+    size_t bytes = 0;
+    int device = -1;
+};
+std::mutex g_arena_mutex;
+Arena g_arena[2];   // 0: workspace, 1: staging (inputs / outputs)
+
+int arena_get(int which, size_t bytes, void **out)
+{
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    Arena &a = g_arena[which];
+    if (a.device != dev || a.bytes < bytes) {
+        if (a.ptr) {
+            cudaSetDevice(a.device);
+            cudaFree(a.ptr);
+            cudaSetDevice(dev);
+            a.ptr = nullptr;
+            a.bytes = 0;
+        }
+        size_t want = align_up(bytes + bytes / 8, 1 << 20);
+        cudaError_t e = cudaMalloc(&a.ptr, want);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            want = align_up(bytes, 1 << 20);
+            e = cudaMalloc(&a.ptr, want);
+        }
+        if (e != cudaSuccess) {
+            a.ptr = nullptr;
+            return fail(FB_ENOMEM, "cudaMalloc of %zu bytes failed: %s", want, cudaGetErrorString(e));
+        }
+        a.bytes = want;
+        a.device = dev;
+    }
+    *out = a.ptr;
+    return FB_OK;
+}
+
+int require_device()
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n < 1) {
+        cudaGetLastError();
+        return fail(FB_ECUDA, "no CUDA device available (%s); this library has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    }
+    return FB_OK;
+}
+
+struct Staging {
+    char *base;
+    size_t off = 0;
+    explicit Staging(char *b) : base(b) {}
+    template <typename T> T *take(size_t n) { T *p = (T *)(base + off); off += align_up(n * sizeof(T)); return p; }
+};
+
+}  // namespace
+
+// ====================================================================================================
+FB_EXPORT const char *fb_last_error(void) { return g_err.c_str(); }
+FB_EXPORT int fb_version(void) { return 100; }
+
+FB_EXPORT int fb_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+FB_EXPORT int fb_set_device(int device)
+{
+    int rc = require_device();
+    if (rc != FB_OK) return rc;
+    CUDA_TRY(cudaSetDevice(device));
+    return FB_OK;
+}
+
+// interpolation.py:549-552
+FB_EXPORT int32_t fb_half_kernel_size_opt(double sigma, double step, int num_iter)
+{
+    const double s = sigma / step;
+    return (int32_t)((std::sqrt(1.0 + 12 * s * s / num_iter) - 1.0) / 2.0);
+}
+
+// interpolation.py:783-785
+FB_EXPORT int32_t fb_half_kernel_size(double sigma, double step, int num_iter)
+{
+    return (int32_t)(std::sqrt(3.0 / num_iter) * sigma / step + 0.5);
+}
+
+// interpolation.py:561-569
+FB_EXPORT double fb_tail_value(double sigma, double step, int num_iter)
+{
+    const long long hks = fb_half_kernel_size_opt(sigma, step, num_iter);
+    const long long ks = 2 * hks + 1;
+    const double sigma_rect_sqr = (double)((hks + 1) * hks) / 3.0 * (step * step);
+    const double hs = (double)(hks + 1) * step;
+    return 0.5 * (double)ks * (sigma * sigma / num_iter - sigma_rect_sqr) / (hs * hs - sigma * sigma / num_iter);
+}
+
+// interpolation.py:424-425
+FB_EXPORT double fb_conv_scale_factor(int dim, const int32_t *kernel_size, const double *tail_value,
+                                      const double *sigma, const double *step, int num_iter,
+                                      double max_dist_weight)
+{
+    double prod = 1.0;
+    for (int m = 0; m < dim; ++m) {
+        const double f = int_power((double)kernel_size[m] + 2 * tail_value[m], num_iter) / std::sqrt(2 * M_PI) /
+                         (sigma[m] / step[m]);
+        prod *= f;
+    }
+    return prod * max_dist_weight;
+}
+
+FB_EXPORT int64_t fb_workspace_bytes(const fb_problem *prob, int64_t nsamples)
+{
+    Derived d;
+    if (derive(prob, d) != FB_OK) return FB_EINVAL;
+    Workspace w;
+    carve(w, nullptr, prob, d.total, nsamples);
+    return (int64_t)w.bytes;
+}
+
+FB_EXPORT int fb_barnes_dev(const fb_problem *prob, int64_t nsamples, const int64_t *sample_offsets,
+                            const double *d_pts, const double *d_val, float *d_out, double *d_out64,
+                            void *d_workspace, int64_t workspace_bytes, void *stream)
+{
+    int rc = require_device();
+    if (rc != FB_OK) return rc;
+    if (!d_pts || !d_val || !d_out || !d_workspace) return fail(FB_EINVAL, "null device pointer");
+    return pipeline(prob, nsamples, sample_offsets, d_pts, d_val, d_out, d_out64, d_workspace, workspace_bytes,
+                    (cudaStream_t)stream, true);
+}
+
+FB_EXPORT int fb_barnes_host(const fb_problem *prob, int64_t nsamples, const int64_t *sample_offsets,
+                             const double *pts, const double *val, float *out, double *out64)
+{
+    int rc = require_device();
+    if (rc != FB_OK) return rc;
+    if (!prob || !pts || !val || !out) return fail(FB_EINVAL, "null pointer");
+    Derived d;
+    if ((rc = derive(prob, d)) != FB_OK) return rc;
+    if ((rc = check_kernel_vs_grid(prob, d)) != FB_OK) return rc;
+    std::lock_guard<std::mutex> lock(g_arena_mutex);
+    Workspace w;
+    carve(w, nullptr, prob, d.total, nsamples);
+    const size_t npts = (size_t)nsamples * prob->dim, ngrid = (size_t)prob->nfields * d.total;
+    const size_t stage_bytes = align_up(npts * 8) + align_up((size_t)nsamples * 8) + align_up(ngrid * 4) +
+                               (out64 ? align_up(ngrid * 8) : 0) + 1024;
+    void *ws = nullptr, *stg = nullptr;
+    if ((rc = arena_get(0, w.bytes, &ws)) != FB_OK) return rc;
+    if ((rc = arena_get(1, stage_bytes, &stg)) != FB_OK) return rc;
+    Staging s((char *)stg);
+    double *d_pts = s.take<double>(npts);
+    double *d_val = s.take<double>((size_t)nsamples);
+    float *d_out = s.take<float>(ngrid);
+    double *d_out64 = out64 ? s.take<double>(ngrid) : nullptr;
+    cudaStream_t st = 0;
+    CUDA_TRY(cudaMemcpyAsync(d_pts, pts, npts * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_val, val, (size_t)nsamples * 8, cudaMemcpyHostToDevice, st));
+    rc = pipeline(prob, nsamples, sample_offsets, d_pts, d_val, d_out, d_out64, ws, (long long)g_arena[0].bytes, st, true);
+    if (rc != FB_OK) return rc;
+    CUDA_TRY(cudaMemcpyAsync(out, d_out, ngrid * 4, cudaMemcpyDeviceToHost, st));
+    if (out64) CUDA_TRY(cudaMemcpyAsync(out64, d_out64, ngrid * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return FB_OK;
+}
+
+// ---- stage entry points -------------------------------------------------------------------------------
+FB_EXPORT int fb_accumulate_lines_host(double *lines, int64_t n_outer, int64_t len, int64_t n_inner,
+                                       int64_t rect_len, int num_iter, double alpha)
+{
+    int rc = require_device();
+    if (rc != FB_OK) return rc;
+    if (!lines || n_outer < 1 || len < 1 || n_inner < 1 || num_iter < 1 || rect_len < 1 || !(rect_len & 1))
+        return fail(FB_EINVAL, "invalid line batch (rect_len must be odd and positive)");
+    std::lock_guard<std::mutex> lock(g_arena_mutex);
+    const size_t n = (size_t)n_outer * len * n_inner;
+    void *stg = nullptr;
+    if ((rc = arena_get(1, 2 * align_up(n * 8) + 1024, &stg)) != FB_OK) return rc;
+    Staging s((char *)stg);
+    Pair cur{s.take<double>(n), nullptr}, spare{s.take<double>(n), nullptr};
+    cudaStream_t st = 0;
+    CUDA_TRY(cudaMemcpyAsync(cur.v, lines, n * 8, cudaMemcpyHostToDevice, st));
+    AxisParams ax{(int)((rect_len - 1) / 2), alpha};
+    rc = run_sweep(0, num_iter, ax, cur, spare, nullptr, nullptr, nullptr, 0.0, n_outer, len, n_inner, false, st);
+    if (rc != FB_OK) return rc;
+    CUDA_TRY(cudaMemcpyAsync(lines, cur.v, n * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return FB_OK;
+}
+
+namespace {
+int launch_transpose(const double *in, double *out, long long n_outer, long long rows, long long cols, cudaStream_t st)
+{
+    // z dimension of the grid is limited to 65535 blocks: loop over slabs of outer indices
+    for (long long o0 = 0; o0 < n_outer; o0 += 65535) {
+        const long long no = n_outer - o0 < 65535 ? n_outer - o0 : 65535;
+        dim3 g((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32), (unsigned)no);
+        if (g.y > 65535) return fail(FB_EINVAL, "grid too tall for the transpose helper");
+        fb_transpose_kernel<<<g, 256, 0, st>>>(in + o0 * rows * cols, out + o0 * rows * cols, no, rows, cols);
+        LAUNCH_CHECK();
+    }
+    return FB_OK;
+}
+}  // namespace
+
+FB_EXPORT int fb_convolve_host(int dim, double *vg, double *wg, const int64_t *size, const int32_t *kernel_size,
+                               int num_iter, const double *tail_value, double conv_scale_factor)
+{
+    int rc = require_device();
+    if (rc != FB_OK) return rc;
+    if (dim < 1 || dim > 3 || !vg || !wg || !size || !kernel_size || num_iter < 1) return fail(FB_EINVAL, "invalid argument");
+    const long long W = size[0], H = dim > 1 ? size[1] : 1, Dz = dim > 2 ? size[2] : 1;
+    const size_t n = (size_t)W * H * Dz;
+    AxisParams ax[3];
+    for (int m = 0; m < dim; ++m) {
+        if (kernel_size[m] < 1 || !(kernel_size[m] & 1)) return fail(FB_EINVAL, "kernel_size must be odd and positive");
+        ax[m].T = (kernel_size[m] - 1) / 2;
+        ax[m].alpha = tail_value ? tail_value[m] : 0.0;
+    }
+    std::lock_guard<std::mutex> lock(g_arena_mutex);
+    void *stg = nullptr;
+    if ((rc = arena_get(1, 4 * align_up(n * 8) + 1024, &stg)) != FB_OK) return rc;
+    Staging s((char *)stg);
+    double *v0 = s.take<double>(n), *w0 = s.take<double>(n), *v1 = s.take<double>(n), *w1 = s.take<double>(n);
+    cudaStream_t st = 0;
+    CUDA_TRY(cudaMemcpyAsync(v0, vg, n * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(w0, wg, n * 8, cudaMemcpyHostToDevice, st));
+    Pair cur{v0, w0}, spare{v1, w1};
+    if (dim == 1) {
+        rc = run_sweep(0, num_iter, ax[0], cur, spare, nullptr, nullptr, nullptr, 0.0, 1, W, 1, true, st);
+        if (rc != FB_OK) return rc;
+    } else {
+        // natural [z][y][x] -> A layout [z][x][y]
+        if ((rc = launch_transpose(v0, v1, Dz, H, W, st)) != FB_OK) return rc;
+        if ((rc = launch_transpose(w0, w1, Dz, H, W, st)) != FB_OK) return rc;
+        cur = Pair{v1, w1};
+        spare = Pair{v0, w0};
+        rc = run_sweep(1, num_iter, ax[0], cur, spare, nullptr, nullptr, nullptr, 0.0, Dz, W, H, true, st);
+        if (rc != FB_OK) return rc;
+        rc = run_sweep(0, num_iter, ax[1], cur, spare, nullptr, nullptr, nullptr, 0.0, Dz, H, W, true, st);
+        if (rc != FB_OK) return rc;
+        if (dim == 3) {
+            rc = run_sweep(0, num_iter, ax[2], cur, spare, nullptr, nullptr, nullptr, 0.0, 1, Dz, H * W, true, st);
+            if (rc != FB_OK) return rc;
+        }
+    }
+    double *rv = cur.v, *rw = cur.w;
+    fb_mask_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(rw, (long long)n, conv_scale_factor);
+    LAUNCH_CHECK();
+    CUDA_TRY(cudaMemcpyAsync(vg, rv, n * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(wg, rw, n * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return FB_OK;
+}
+
+FB_EXPORT int fb_inject_host(const fb_problem *prob, int64_t nsamples, const int64_t *sample_offsets,
+                             const double *pts, const double *val, double *vg, double *wg, double *offsets)
+{
+    int rc = require_device();
+    if (rc != FB_OK) return rc;
+    if (!prob || !pts || !val || !vg || !wg) return fail(FB_EINVAL, "null pointer");
+    Derived d;
+    if ((rc = derive(prob, d)) != FB_OK) return rc;
+    std::lock_guard<std::mutex> lock(g_arena_mutex);
+    Workspace w;
+    carve(w, nullptr, prob, d.total, nsamples);
+    const size_t npts = (size_t)nsamples * prob->dim, ngrid = (size_t)prob->nfields * d.total;
+    // dim 1 has no B buffers in the workspace: stage the transposed copies separately
+    const size_t stage_bytes = align_up(npts * 8) + align_up((size_t)nsamples * 8) + 2 * align_up(ngrid * 8) + 1024;
+    void *ws = nullptr, *stg = nullptr;
+    if ((rc = arena_get(0, w.bytes, &ws)) != FB_OK) return rc;
+    if ((rc = arena_get(1, stage_bytes, &stg)) != FB_OK) return rc;
+    carve(w, (char *)ws, prob, d.total, nsamples);
+    Staging s((char *)stg);
+    double *d_pts = s.take<double>(npts);
+    double *d_val = s.take<double>((size_t)nsamples);
+    double *tv = s.take<double>(ngrid), *tw = s.take<double>(ngrid);
+    cudaStream_t st = 0;
+    CUDA_TRY(cudaMemcpyAsync(d_pts, pts, npts * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_val, val, (size_t)nsamples * 8, cudaMemcpyHostToDevice, st));
+    if ((rc = run_inject(prob, d, nsamples, sample_offsets, d_pts, d_val, w, st)) != FB_OK) return rc;
+    const double *rv = w.vA, *rw = w.wA;
+    if (prob->dim > 1) {
+        // A layout [..][x][y] -> natural [..][y][x]
+        if ((rc = launch_transpose(w.vA, tv, prob->nfields * d.Dz, d.W, d.H, st)) != FB_OK) return rc;
+        if ((rc = launch_transpose(w.wA, tw, prob->nfields * d.Dz, d.W, d.H, st)) != FB_OK) return rc;
+        rv = tv;
+        rw = tw;
+    }
+    CUDA_TRY(cudaMemcpyAsync(vg, rv, ngrid * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(wg, rw, ngrid * 8, cudaMemcpyDeviceToHost, st));
+    std::vector<unsigned long long> mm((size_t)prob->nfields * FB_MM_STRIDE);
+    CUDA_TRY(cudaMemcpyAsync(mm.data(), w.mm, mm.size() * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (offsets) {
+        for (long long b = 0; b < prob->nfields; ++b) {
+            const unsigned long long *m = &mm[(size_t)b * FB_MM_STRIDE];
+            auto dec = [](unsigned long long k) {
+                unsigned long long u = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+                double v;
+                memcpy(&v, &u, 8);
+                return v;
+            };
+            offsets[b] = m[2] ? NAN : (dec(m[0]) + dec(m[1])) / 2.0;
+        }
+    }
+    return FB_OK;
+}
+
+// ---- S2 -------------------------------------------------------------------------------------------------
+// util/lambert_conformal.py:50-94 (host libm, like the Numba code)
+FB_EXPORT int fb_lambert_create_proj(double center_lon, double center_lat, double lat1, double lat2, double *proj)
+{
+    if (!proj) return fail(FB_EINVAL, "null pointer");
+    const double RAD = M_PI / 180.0, HALF = RAD / 2.0;
+    double n;
+    if (lat1 != lat2)
+        n = std::log(std::cos(lat1 * RAD) / std::cos(lat2 * RAD)) /
+            std::log(std::tan((90.0 + lat2) * HALF) / std::tan((90.0 + lat1) * HALF));
+    else
+        n = std::sin(lat1 * RAD);
+    const double n_inv = 1.0 / n;
+    const double F = std::cos(lat1 * RAD) * std::pow(std::tan((90.0 + lat1) * HALF), n) / n;
+    const double rho0 = F / std::pow(std::tan((90.0 + center_lat) * HALF), n);
+    proj[0] = center_lon; proj[1] = n; proj[2] = n_inv; proj[3] = F; proj[4] = rho0;
+    return FB_OK;
+}
+
+namespace {
+FbProj make_proj(const double *proj) { return FbProj{proj[0], proj[1], proj[2], proj[3], proj[4]}; }
+
+int resample_dev(const float *d_lam, long long lamW, long long lamH, const double *lam_x0, const double *x0,
+                 const double *step, const int64_t *size, const double *proj, double *d_tab, float *d_res, cudaStream_t st)
+{
+    const long long W = size[0], H = size[1];
+    if (H > 65535) return fail(FB_EINVAL, "output grid too tall for the resampling launch: %lld", H);
+    FbProj pr = make_proj(proj);
+    fb_resample_tables_kernel<<<(unsigned)((W + H + 255) / 256), 256, 0, st>>>(d_tab, W, H, x0[0], x0[1], step[0], step[1], pr);
+    LAUNCH_CHECK();
+    fb_resample_kernel<<<dim3((unsigned)((W + 255) / 256), (unsigned)H), 256, 0, st>>>(
+        d_lam, lamW, lamH, d_tab, d_res, W, H, lam_x0[0], lam_x0[1], step[0], step[1], pr);
+    LAUNCH_CHECK();
+    return FB_OK;
+}
+
+void s2_problem(fb_problem &p, const double *sigma, const double *step, int num_iter, double mdw)
+{
+    memset(&p, 0, sizeof p);
+    p.dim = 2;
+    p.method = FB_METHOD_OPTIMIZED_CONVOLUTION;
+    p.num_iter = num_iter;
+    p.nfields = 1;
+    // interpolationS2.py:187-188: the fixed grid in Lambert space
+    p.size[0] = (int64_t)(64.0 / step[0]);
+    p.size[1] = (int64_t)(44.0 / step[1]);
+    p.size[2] = 1;
+    p.x0[0] = -32.0;
+    p.x0[1] = -2.0;
+    for (int m = 0; m < 2; ++m) { p.sigma[m] = sigma[m]; p.step[m] = step[m]; }
+    p.max_dist_weight = mdw;
+}
+
+// part1 on the device: d_lam receives the Lambert field; returns the staging layout it used
+int s2_part1_dev(const fb_problem &lp, long long nsamples, const double *d_pts, double *d_lam_pts, const double *d_val,
+                 const double *proj, float *d_lam, void *ws, long long ws_bytes, cudaStream_t st)
+{
+    if (nsamples > 0) {
+        fb_lambert_to_map_kernel<<<(unsigned)((nsamples + 255) / 256), 256, 0, st>>>(d_pts, d_lam_pts, nsamples, make_proj(proj));
+        LAUNCH_CHECK();
+    }
+    // the S2 path has no kernel-size-vs-grid check (interpolationS2.py:131-132)
+    return pipeline(&lp, nsamples, nullptr, d_lam_pts, d_val, d_lam, nullptr, ws, ws_bytes, st, false);
+}
+}  // namespace
+
+FB_EXPORT int fb_lambert_to_map_host(const double *geoc, double *mapc, int64_t n, const double *proj)
+{
+    int rc = require_device();
+    if (rc != FB_OK) return rc;
+    if (!geoc || !mapc || !proj || n < 0) return fail(FB_EINVAL, "invalid argument");
+    if (n == 0) return FB_OK;
+    std::lock_guard<std::mutex> lock(g_arena_mutex);
+    void *stg = nullptr;
+    if ((rc = arena_get(1, 2 * align_up((size_t)n * 16) + 1024, &stg)) != FB_OK) return rc;
+    Staging s((char *)stg);
+    double *d_in = s.take<double>((size_t)n * 2), *d_out = s.take<double>((size_t)n * 2);
+    cudaStream_t st = 0;
+    CUDA_TRY(cudaMemcpyAsync(d_in, geoc, (size_t)n * 16, cudaMemcpyHostToDevice, st));
+    fb_lambert_to_map_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_in, d_out, n, make_proj(proj));
+    LAUNCH_CHECK();
+    CUDA_TRY(cudaMemcpyAsync(mapc, d_out, (size_t)n * 16, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return FB_OK;
+}
+
+FB_EXPORT int fb_s2_part1_host(int64_t nsamples, const double *pts, const double *val, const double *sigma,
+                               const double *step, int num_iter, double max_dist_weight, const double *proj,
+                               float *lam_field)
+{
+    int rc = require_device();
+    if (rc != FB_OK) return rc;
+    if (!pts || !val || !sigma || !step || !proj || !lam_field) return fail(FB_EINVAL, "null pointer");
+    fb_problem lp;
+    s2_problem(lp, sigma, step, num_iter, max_dist_weight);
+    Derived d;
+    if ((rc = derive(&lp, d)) != FB_OK) return rc;
+    std::lock_guard<std::mutex> lock(g_arena_mutex);
+    Workspace w;
+    carve(w, nullptr, &lp, d.total, nsamples);
+    const size_t stage_bytes = 2 * align_up((size_t)nsamples * 16) + align_up((size_t)nsamples * 8) + align_up((size_t)d.total * 4) + 1024;
+    void *ws = nullptr, *stg = nullptr;
+    if ((rc = arena_get(0, w.bytes, &ws)) != FB_OK) return rc;
+    if ((rc = arena_get(1, stage_bytes, &stg)) != FB_OK) return rc;
+    Staging s((char *)stg);
+    double *d_pts = s.take<double>((size_t)nsamples * 2), *d_lpts = s.take<double>((size_t)nsamples * 2);
+    double *d_val = s.take<double>((size_t)nsamples);
+    float *d_lam = s.take<float>((size_t)d.total);
+    cudaStream_t st = 0;
+    CUDA_TRY(cudaMemcpyAsync(d_pts, pts, (size_t)nsamples * 16, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_val, val, (size_t)nsamples * 8, cudaMemcpyHostToDevice, st));
+    if ((rc = s2_part1_dev(lp, nsamples, d_pts, d_lpts, d_val, proj, d_lam, ws, (long long)g_arena[0].bytes, st)) != FB_OK) return rc;
+    CUDA_TRY(cudaMemcpyAsync(lam_field, d_lam, (size_t)d.total * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return FB_OK;
+}
+
+FB_EXPORT int fb_s2_resample_host(const float *lam_field, int64_t lam_w, int64_t lam_h, const double *lam_x0,
+                                  const double *x0, const double *step, const int64_t *size, const double *proj,
+                                  float *res)
+{
+    int rc = require_device();
+    if (rc != FB_OK) return rc;
+    if (!lam_field || !lam_x0 || !x0 || !step || !size || !proj || !res) return fail(FB_EINVAL, "null pointer");
+    std::lock_guard<std::mutex> lock(g_arena_mutex);
+    const size_t nl = (size_t)lam_w * lam_h, no = (size_t)size[0] * size[1];
+    void *stg = nullptr;
+    if ((rc = arena_get(1, align_up(nl * 4) + align_up(no * 4) + align_up((size_t)(2 * size[0] + size[1]) * 8) + 1024, &stg)) != FB_OK) return rc;
+    Staging s((char *)stg);
+    float *d_lam = s.take<float>(nl), *d_res = s.take<float>(no);
+    double *d_tab = s.take<double>((size_t)(2 * size[0] + size[1]));
+    cudaStream_t st = 0;
+    CUDA_TRY(cudaMemcpyAsync(d_lam, lam_field, nl * 4, cudaMemcpyHostToDevice, st));
+    if ((rc = resample_dev(d_lam, lam_w, lam_h, lam_x0, x0, step, size, proj, d_tab, d_res, st)) != FB_OK) return rc;
+    CUDA_TRY(cudaMemcpyAsync(res, d_res, no * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return FB_OK;
+}
+
+FB_EXPORT int fb_barnes_s2_host(int64_t nsamples, const double *pts, const double *val, const double *sigma,
+                                const double *x0, const double *step, const int64_t *size, int num_iter,
+                                double max_dist_weight, const double *proj, float *res)
+{
+    int rc = require_device();
+    if (rc != FB_OK) return rc;
+    if (!pts || !val || !sigma || !x0 || !step || !size || !proj || !res) return fail(FB_EINVAL, "null pointer");
+    fb_problem lp;
+    s2_problem(lp, sigma, step, num_iter, max_dist_weight);
+    Derived d;
+    if ((rc = derive(&lp, d)) != FB_OK) return rc;
+    std::lock_guard<std::mutex> lock(g_arena_mutex);
+    Workspace w;
+    carve(w, nullptr, &lp, d.total, nsamples);
+    const size_t no = (size_t)size[0] * size[1];
+    const size_t stage_bytes = 2 * align_up((size_t)nsamples * 16) + align_up((size_t)nsamples * 8) + align_up((size_t)d.total * 4) +
+                               align_up(no * 4) + align_up((size_t)(2 * size[0] + size[1]) * 8) + 1024;
+    void *ws = nullptr, *stg = nullptr;
+    if ((rc = arena_get(0, w.bytes, &ws)) != FB_OK) return rc;
+    if ((rc = arena_get(1, stage_bytes, &stg)) != FB_OK) return rc;
+    Staging s((char *)stg);
+    double *d_pts = s.take<double>((size_t)nsamples * 2), *d_lpts = s.take<double>((size_t)nsamples * 2);
+    double *d_val = s.take<double>((size_t)nsamples);
+    float *d_lam = s.take<float>((size_t)d.total), *d_res = s.take<float>(no);
+    double *d_tab = s.take<double>((size_t)(2 * size[0] + size[1]));
+    cudaStream_t st = 0;
+    CUDA_TRY(cudaMemcpyAsync(d_pts, pts, (size_t)nsamples * 16, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_val, val, (size_t)nsamples * 8, cudaMemcpyHostToDevice, st));
+    if ((rc = s2_part1_dev(lp, nsamples, d_pts, d_lpts, d_val, proj, d_lam, ws, (long long)g_arena[0].bytes, st)) != FB_OK) return rc;
+    const double lam_x0[2] = {lp.x0[0], lp.x0[1]};
+    if ((rc = resample_dev(d_lam, lp.size[0], lp.size[1], lam_x0, x0, step, size, proj, d_tab, d_res, st)) != FB_OK) return rc;
+    CUDA_TRY(cudaMemcpyAsync(res, d_res, no * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return FB_OK;
+}
+
+// ---- introspection ------------------------------------------------------------------------------------------
+FB_EXPORT int64_t fb_kernel_launch_count(void) { return g_launches.load(); }
+
+FB_EXPORT int fb_set_profiling(int enabled)
+{
+    g_profiling.store(enabled ? 1 : 0);
+    return FB_OK;
+}
+
+FB_EXPORT int fb_last_profile(double *ms_segments, int nsegments, int64_t *launches)
+{
+    if (!g_prof.armed) return fail(FB_EINVAL, "no profiled call recorded on this thread (fb_set_profiling(1) first)");
+    if (g_prof.marked < 2) return fail(FB_EINVAL, "profile incomplete");
+    CUDA_TRY(cudaEventSynchronize(g_prof.ev[g_prof.marked - 1]));
+    for (int i = 0; i < nsegments; ++i) {
+        float ms = 0.f;
+        if (i < kProfSegments && i + 1 < g_prof.marked) CUDA_TRY(cudaEventElapsedTime(&ms, g_prof.ev[i], g_prof.ev[i + 1]));
+        if (ms_segments) ms_segments[i] = ms;
+    }
+    if (launches) *launches = g_prof.launches_end - g_prof.launches_begin;
+    return FB_OK;
+}

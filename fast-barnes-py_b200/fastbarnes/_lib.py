@@ -1,0 +1,121 @@
+# -*- coding: utf-8 -*-
+"""
+ctypes binding of the C ABI declared in include/fastbarnes_b200.h
+(csrc/_build/libfastbarnes_b200.so, hand-written sm_100a CUDA kernels).
+
+There is no CPU fallback: if the shared library cannot be found (and cannot be built
+because nvcc is absent) importing this module fails, and every compute call raises
+RuntimeError when no CUDA device is present.
+"""
+import ctypes
+import os
+import shutil
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.normpath(os.path.join(_HERE, '..', 'csrc'))
+LIB_PATH = os.path.join(CSRC, '_build', 'libfastbarnes_b200.so')
+
+FB_OK, FB_EINVAL, FB_ECUDA, FB_ENOMEM, FB_EKERNEL = 0, -1, -2, -3, -4
+METHOD_OPTIMIZED_CONVOLUTION, METHOD_CONVOLUTION = 0, 1
+
+c_double_p = ctypes.POINTER(ctypes.c_double)
+c_float_p = ctypes.POINTER(ctypes.c_float)
+c_i64_p = ctypes.POINTER(ctypes.c_int64)
+c_i32_p = ctypes.POINTER(ctypes.c_int32)
+
+
+class FbProblem(ctypes.Structure):
+    """ struct fb_problem (include/fastbarnes_b200.h). """
+    _fields_ = [('dim', ctypes.c_int32), ('method', ctypes.c_int32), ('num_iter', ctypes.c_int32),
+                ('flags', ctypes.c_int32), ('nfields', ctypes.c_int64), ('size', ctypes.c_int64 * 3),
+                ('sigma', ctypes.c_double * 3), ('x0', ctypes.c_double * 3), ('step', ctypes.c_double * 3),
+                ('max_dist_weight', ctypes.c_double)]
+
+
+# every symbol include/fastbarnes_b200.h declares: name -> (restype, argtypes)
+SIGNATURES = {
+    'fb_last_error': (ctypes.c_char_p, []),
+    'fb_version': (ctypes.c_int, []),
+    'fb_device_count': (ctypes.c_int, []),
+    'fb_set_device': (ctypes.c_int, [ctypes.c_int]),
+    'fb_half_kernel_size_opt': (ctypes.c_int32, [ctypes.c_double, ctypes.c_double, ctypes.c_int]),
+    'fb_half_kernel_size': (ctypes.c_int32, [ctypes.c_double, ctypes.c_double, ctypes.c_int]),
+    'fb_tail_value': (ctypes.c_double, [ctypes.c_double, ctypes.c_double, ctypes.c_int]),
+    'fb_conv_scale_factor': (ctypes.c_double, [ctypes.c_int, c_i32_p, c_double_p, c_double_p, c_double_p,
+                                               ctypes.c_int, ctypes.c_double]),
+    'fb_barnes_host': (ctypes.c_int, [ctypes.POINTER(FbProblem), ctypes.c_int64, c_i64_p, ctypes.c_void_p,
+                                      ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    'fb_workspace_bytes': (ctypes.c_int64, [ctypes.POINTER(FbProblem), ctypes.c_int64]),
+    'fb_barnes_dev': (ctypes.c_int, [ctypes.POINTER(FbProblem), ctypes.c_int64, c_i64_p, ctypes.c_void_p,
+                                     ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                     ctypes.c_int64, ctypes.c_void_p]),
+    'fb_accumulate_lines_host': (ctypes.c_int, [c_double_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
+                                                ctypes.c_int64, ctypes.c_int, ctypes.c_double]),
+    'fb_convolve_host': (ctypes.c_int, [ctypes.c_int, c_double_p, c_double_p, c_i64_p, c_i32_p, ctypes.c_int,
+                                        c_double_p, ctypes.c_double]),
+    'fb_inject_host': (ctypes.c_int, [ctypes.POINTER(FbProblem), ctypes.c_int64, c_i64_p, c_double_p,
+                                      c_double_p, c_double_p, c_double_p, c_double_p]),
+    'fb_lambert_create_proj': (ctypes.c_int, [ctypes.c_double] * 4 + [c_double_p]),
+    'fb_lambert_to_map_host': (ctypes.c_int, [c_double_p, c_double_p, ctypes.c_int64, c_double_p]),
+    'fb_s2_part1_host': (ctypes.c_int, [ctypes.c_int64, c_double_p, c_double_p, c_double_p, c_double_p,
+                                        ctypes.c_int, ctypes.c_double, c_double_p, c_float_p]),
+    'fb_s2_resample_host': (ctypes.c_int, [c_float_p, ctypes.c_int64, ctypes.c_int64, c_double_p, c_double_p,
+                                           c_double_p, c_i64_p, c_double_p, c_float_p]),
+    'fb_barnes_s2_host': (ctypes.c_int, [ctypes.c_int64, c_double_p, c_double_p, c_double_p, c_double_p,
+                                         c_double_p, c_i64_p, ctypes.c_int, ctypes.c_double, c_double_p,
+                                         c_float_p]),
+    'fb_kernel_launch_count': (ctypes.c_int64, []),
+    'fb_set_profiling': (ctypes.c_int, [ctypes.c_int]),
+    'fb_last_profile': (ctypes.c_int, [c_double_p, ctypes.c_int, c_i64_p]),
+}
+
+
+def build(force=False):
+    """ Compiles csrc/ for sm_100a with nvcc (in-tree, csrc/_build/). """
+    srcs = [os.path.join(CSRC, f) for f in ('fb_api.cu', 'fb_kernels.cuh')]
+    srcs.append(os.path.normpath(os.path.join(CSRC, '..', '..', 'include', 'fastbarnes_b200.h')))
+    stale = (not os.path.exists(LIB_PATH)) or any(
+        os.path.exists(s) and os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)
+    if force or stale:
+        nvcc = shutil.which('nvcc') or '/usr/local/cuda/bin/nvcc'
+        if not os.path.exists(nvcc):
+            raise RuntimeError('libfastbarnes_b200.so is missing or stale and nvcc was not found to build it')
+        subprocess.check_call(['make', '-C', CSRC, '-s', 'NVCC=' + nvcc] + (['-B'] if force else []))
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    """ Returns the loaded shared library with argument types set (loads / builds on first use). """
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            build()
+        try:
+            L = ctypes.CDLL(LIB_PATH)
+        except OSError as e:
+            raise RuntimeError('cannot load the CUDA library %s: %s (no CPU fallback exists)' % (LIB_PATH, e))
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def last_error():
+    msg = lib().fb_last_error()
+    return msg.decode('utf-8', 'replace') if msg else ''
+
+
+def check(rc):
+    """ Maps a C return code to the RuntimeError the reference would raise. """
+    if rc != FB_OK:
+        raise RuntimeError(last_error() or ('fastbarnes_b200 error code %d' % rc))
+
+
+def dptr(a):
+    return a.ctypes.data_as(c_double_p)

@@ -1,0 +1,153 @@
+/*
+ * fastbarnes_b200.h -- C ABI of the B200-native optimized-convolution Barnes interpolation.
+ *
+ * Drop-in boundary for ONE path of MeteoSwiss/fast-barnes-py (v2.0.0):
+ *   fastbarnes.interpolation.barnes(..., method='optimized_convolution' | 'convolution')
+ *   fastbarnes.interpolationS2.barnes_S2(..., method='optimized_convolution_S2')
+ * The reference has no FFI of its own (it is Python + Numba @njit); its boundary is the
+ * Python call surface.  Each entry point below cites the reference function it replaces
+ * (paths relative to the reference root).  The Python side that binds these symbols with
+ * ctypes lives in fast-barnes-py_b200/fastbarnes/ (see INTEGRATION.md).
+ *
+ * Conventions
+ *   - plain C types only; no torch / CUDA types in the signatures (a CUDA stream is passed
+ *     as void*; NULL = the legacy default stream).
+ *   - every function returns FB_OK (0) or a negative FB_E* code; fb_last_error() returns a
+ *     thread-local message for the last failure.
+ *   - `*_host` entry points take HOST pointers and are synchronous (H2D, kernels, D2H inside);
+ *     `*_dev` entry points take DEVICE pointers plus a caller-provided workspace and only
+ *     enqueue work on the stream.
+ *   - grids are returned with reversed dimensions like the reference: [x], [y][x], [z][y][x],
+ *     float32, NaN where the convolved weight is below the max_dist threshold.
+ *   - fields: a call may carry `nfields` independent fields (time steps / ensemble members)
+ *     on the same grid.  Samples of all fields are concatenated; field b owns the samples
+ *     [sample_offsets[b], sample_offsets[b+1]).  nfields == 1 is the reference call.
+ *   - there is no CPU fallback: without a CUDA device every compute entry returns FB_ECUDA.
+ */
+#ifndef FASTBARNES_B200_H
+#define FASTBARNES_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FB_OK        0
+#define FB_EINVAL   -1   /* invalid argument */
+#define FB_ECUDA    -2   /* CUDA runtime error / no device */
+#define FB_ENOMEM   -3   /* workspace too small / allocation failed */
+#define FB_EKERNEL  -4   /* rectangular kernel does not fit (grid or on-chip ring storage) */
+
+#define FB_METHOD_OPTIMIZED_CONVOLUTION 0   /* interpolation.py:169-176 */
+#define FB_METHOD_CONVOLUTION           1   /* interpolation.py:178-185 */
+
+/* Problem description shared by the interpolation entry points
+ * (the arguments of _interpolate_opt_convol, interpolation.py:329). */
+typedef struct fb_problem {
+    int32_t dim;             /* 1, 2 or 3 */
+    int32_t method;          /* FB_METHOD_* */
+    int32_t num_iter;        /* number of self-convolutions n */
+    int32_t flags;           /* reserved, 0 */
+    int64_t nfields;         /* independent fields on the same grid (>= 1) */
+    int64_t size[3];         /* grid extension (x, y, z) */
+    double  sigma[3];        /* Gaussian width per axis */
+    double  x0[3];           /* grid start point */
+    double  step[3];         /* grid step per axis */
+    double  max_dist_weight; /* exp(-max_dist^2/2), interpolation.py:167 */
+} fb_problem;
+
+/* ---- library / device -------------------------------------------------------------------- */
+const char *fb_last_error(void);
+int  fb_version(void);
+/* number of visible CUDA devices (0 if none / driver missing) */
+int  fb_device_count(void);
+/* selects the CUDA device used by the calling thread's subsequent calls */
+int  fb_set_device(int device);
+
+/* ---- kernel parameters (host arithmetic, bit-identical to the Numba expressions) --------- */
+/* interpolation.py:549-552  _get_half_kernel_size_opt */
+int32_t fb_half_kernel_size_opt(double sigma, double step, int num_iter);
+/* interpolation.py:783-785  _get_half_kernel_size */
+int32_t fb_half_kernel_size(double sigma, double step, int num_iter);
+/* interpolation.py:561-569  _get_tail_value */
+double  fb_tail_value(double sigma, double step, int num_iter);
+/* interpolation.py:424-425 (== :389-390, :472-473, and :634-635 with tail 0) conv_scale_factor */
+double  fb_conv_scale_factor(int dim, const int32_t *kernel_size, const double *tail_value,
+                             const double *sigma, const double *step, int num_iter,
+                             double max_dist_weight);
+
+/* ---- whole path, HOST buffers ------------------------------------------------------------- */
+/* interpolation.py:329-367 _interpolate_opt_convol (method 0) / :575-612 _interpolate_convol
+ * (method 1) for prob->nfields fields.
+ *   pts  [nsamples][dim] float64, val [nsamples] float64 (not modified),
+ *   sample_offsets [nfields+1] or NULL (NULL: equal split, nsamples % nfields == 0),
+ *   out  [nfields][prod(size)] float32, index order z,y,x,
+ *   out64 optional (may be NULL): the pre-cast fp64 quotient vg/wg+offset, same layout.  */
+int fb_barnes_host(const fb_problem *prob, int64_t nsamples, const int64_t *sample_offsets,
+                   const double *pts, const double *val, float *out, double *out64);
+
+/* ---- whole path, DEVICE buffers ----------------------------------------------------------- */
+/* bytes of scratch fb_barnes_dev needs for this problem and sample count */
+int64_t fb_workspace_bytes(const fb_problem *prob, int64_t nsamples);
+/* Same computation as fb_barnes_host with every pointer in device memory; sample_offsets is a
+ * HOST pointer (or NULL).  Enqueues on `stream` and returns without synchronising.          */
+int fb_barnes_dev(const fb_problem *prob, int64_t nsamples, const int64_t *sample_offsets,
+                  const double *d_pts, const double *d_val, float *d_out, double *d_out64,
+                  void *d_workspace, int64_t workspace_bytes, void *stream);
+
+/* ---- stages (private-but-tested functions of the reference) -------------------------------- */
+/* interpolation.py:485-533 _accumulate_tail_array (alpha) / :729-772 _accumulate_array
+ * (alpha = 0) applied in place to n_outer*n_inner independent lines of length len stored as
+ * lines[outer][k][inner] (inner contiguous), HOST memory.  rect_len = 2T+1.               */
+int fb_accumulate_lines_host(double *lines, int64_t n_outer, int64_t len, int64_t n_inner,
+                             int64_t rect_len, int num_iter, double alpha);
+/* interpolation.py:373-479 _convolve_tail_{1,2,3}d / :617-724 _convolve_{1,2,3}d: in place on
+ * HOST grids vg, wg [z][y][x]; weights below conv_scale_factor become NaN.                 */
+int fb_convolve_host(int dim, double *vg, double *wg, const int64_t *size,
+                     const int32_t *kernel_size, int num_iter, const double *tail_value,
+                     double conv_scale_factor);
+/* interpolation.py:205-212 + :219-322: centre the values (offset returned per field) and inject
+ * them; vg, wg [nfields][z][y][x] HOST grids receive the injected fields.                   */
+int fb_inject_host(const fb_problem *prob, int64_t nsamples, const int64_t *sample_offsets,
+                   const double *pts, const double *val, double *vg, double *wg, double *offsets);
+
+/* ---- S2 path ------------------------------------------------------------------------------ */
+/* util/lambert_conformal.py:50-94 create_proj -> proj[5] = (center_lon, n, n_inv, F, rho0) */
+int fb_lambert_create_proj(double center_lon, double center_lat, double lat1, double lat2,
+                           double *proj);
+/* util/lambert_conformal.py:113-123 to_map: geoc, mapc [n][2] HOST */
+int fb_lambert_to_map_host(const double *geoc, double *mapc, int64_t n, const double *proj);
+/* interpolationS2.py:180-196 interpolate_opt_convol_S2_part1: project the samples, run the
+ * optimized convolution on the fixed Lambert grid lam_x0 = (-32,-2), lam_size =
+ * (int(64/step0), int(44/step1)); lam_field [lam_size1][lam_size0] float32 HOST.           */
+int fb_s2_part1_host(int64_t nsamples, const double *pts, const double *val, const double *sigma,
+                     const double *step, int num_iter, double max_dist_weight,
+                     const double *proj, float *lam_field);
+/* interpolationS2.py:212-254 _resample (part2): bilinear resampling of the Lambert field to
+ * the lon/lat grid; res [size1][size0] float32 HOST.                                        */
+int fb_s2_resample_host(const float *lam_field, int64_t lam_w, int64_t lam_h, const double *lam_x0,
+                        const double *x0, const double *step, const int64_t *size,
+                        const double *proj, float *res);
+/* interpolationS2.py:144-177 _interpolate_opt_convol_S2 with resample=True: part1 + part2 with
+ * the Lambert field kept on the device; res [size1][size0] float32 HOST.                    */
+int fb_barnes_s2_host(int64_t nsamples, const double *pts, const double *val, const double *sigma,
+                      const double *x0, const double *step, const int64_t *size, int num_iter,
+                      double max_dist_weight, const double *proj, float *res);
+
+/* ---- introspection for benchmarks --------------------------------------------------------- */
+/* number of kernels launched by this library in the calling process so far */
+int64_t fb_kernel_launch_count(void);
+/* With profiling enabled (fb_set_profiling(1)) the interpolation entry points bracket their
+ * stages with CUDA events on the launching stream.  fb_last_profile waits for the last call of
+ * the calling thread and returns the duration (ms) of up to 5 segments:
+ *   [0] zero-fill + init  [1] min/max + injection  [2] x sweep  [3] y sweep  [4] z sweep
+ * (absent sweeps report 0) and the number of kernels that call launched.                     */
+int  fb_set_profiling(int enabled);
+int  fb_last_profile(double *ms_segments, int nsegments, int64_t *launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FASTBARNES_B200_H */

@@ -1,0 +1,447 @@
+# -*- coding: utf-8 -*-
+"""
+GPU parity tests (run on the B200 box: pytest -m gpu).  Every call goes through the C ABI
+(include/fastbarnes_b200.h) via the package's ctypes layer; results are compared with the
+committed golden fixtures (outputs of the unmodified reference, oracle/gen_golden.py) and with
+the CPU oracle on seeded inputs.
+
+Tolerances: fp64 path -- BIT-EXACT (float64 quotient and float32 field), stronger than the
+1e-12 relative of the north star.  S2 path: coordinates go through CUDA's tan/pow/sin/cos
+(<= 2 ulp, not libm), so the float32 fields may differ from the reference by rounding flips:
+tolerance 2e-6 relative (~16 float32 ulp at 1000 hPa is never reached; measured max is 1 ulp).
+"""
+import hashlib
+from math import exp, sqrt, pi
+
+import numpy as np
+import pytest
+
+from conftest import load_golden, bits_equal, same_up_to_zero_sign, CASES
+
+pytestmark = pytest.mark.gpu
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+@pytest.fixture(scope='module')
+def fb():
+    from fastbarnes import interpolation
+    return interpolation
+
+
+@pytest.fixture(scope='module')
+def fbS2():
+    from fastbarnes import interpolationS2
+    return interpolationS2
+
+
+@pytest.fixture(scope='module')
+def orc():
+    from oracle import oracle
+    return oracle
+
+
+# ---------------------------------------------------------------------------------------------
+# line kernel: the reference's own known-answer tests (tests/AccumulationTest.py:88-165)
+
+def test_accumulate_tail_array_1_fold(fb):
+    size = 32
+    h_arr = np.empty(size)
+    in_arr = np.zeros(size); in_arr[10] = 1
+    out = fb._accumulate_tail_array(in_arr, h_arr, size, 7, 1, 0.25)
+    assert np.all(out[:6] == 0) and np.all(out[15:] == 0)
+    assert np.array_equal(out[6:15], [0.25, 1, 1, 1, 1, 1, 1, 1, 0.25])
+    in_arr = np.zeros(size); in_arr[2] = 1
+    out = fb._accumulate_tail_array(in_arr, h_arr, size, 7, 1, 0.25)
+    assert np.array_equal(out[:7], [1, 1, 1, 1, 1, 1, 0.25]) and np.all(out[7:] == 0)
+    in_arr = np.zeros(size); in_arr[30] = 1
+    out = fb._accumulate_tail_array(in_arr, h_arr, size, 7, 1, 0.25)
+    assert np.all(out[:26] == 0) and np.array_equal(out[26:], [0.25, 1, 1, 1, 1, 1])
+
+
+def test_accumulate_tail_array_2_fold(fb):
+    size = 32
+    h_arr = np.empty(size)
+    in_arr = np.zeros(size); in_arr[16] = 1
+    out = fb._accumulate_tail_array(in_arr, h_arr, size, 7, 2, 0.5)
+    assert np.all(out[:8] == 0) and np.all(out[25:] == 0)
+    assert np.array_equal(out[8:25], [0.25, 1, 2, 3, 4, 5, 6, 7, 7.5, 7, 6, 5, 4, 3, 2, 1, 0.25])
+    in_arr = np.zeros(size); in_arr[2] = 1
+    out = fb._accumulate_tail_array(in_arr, h_arr, size, 7, 2, 0.5)
+    assert np.array_equal(out[:11], [4.5, 5.5, 6.25, 6.5, 6, 5, 4, 3, 2, 1, 0.25]) and np.all(out[11:] == 0)
+    in_arr = np.zeros(size); in_arr[30] = 1
+    out = fb._accumulate_tail_array(in_arr, h_arr, size, 7, 2, 0.5)
+    assert np.all(out[:22] == 0) and np.array_equal(out[22:], [0.25, 1, 2, 3, 4, 5, 5.5, 5.5, 5.25, 4.5])
+
+
+def test_accumulate_array_folds(fb):
+    size = 32
+    h_arr = np.empty(size)
+    in_arr = np.zeros(size); in_arr[10] = 1
+    out = fb._accumulate_array(in_arr, h_arr, size, 9, 1)
+    assert np.all(out[:6] == 0) and np.all(out[6:15] == 1) and np.all(out[15:] == 0)
+    in_arr = np.zeros(size); in_arr[16] = 1
+    out = fb._accumulate_array(in_arr, h_arr, size, 9, 2)
+    assert np.array_equal(out[8:25], [1, 2, 3, 4, 5, 6, 7, 8, 9, 8, 7, 6, 5, 4, 3, 2, 1])
+    in_arr = np.zeros(size); in_arr[2] = 1
+    out = fb._accumulate_array(in_arr, h_arr, size, 9, 2)
+    assert np.array_equal(out[:11], [5, 6, 7, 7, 7, 6, 5, 4, 3, 2, 1]) and np.all(out[11:] == 0)
+    in_arr = np.zeros(size); in_arr[30] = 1
+    out = fb._accumulate_array(in_arr, h_arr, size, 9, 2)
+    assert np.all(out[:22] == 0) and np.array_equal(out[22:], [1, 2, 3, 4, 5, 6, 6, 6, 6, 5])
+
+
+def test_accumulate_array_versions(fb):
+    size = 32
+    h_arr = np.empty(size)
+    in_arr = np.zeros(size)
+    in_arr[3] = 1; in_arr[9] = 2.5; in_arr[21] = -1.25; in_arr[30] = 1
+    a = fb._accumulate_array(np.copy(in_arr), h_arr, size, 9, 3).copy()
+    b = fb._accumulate_tail_array(np.copy(in_arr), h_arr, size, 9, 3, 0).copy()
+    assert np.array_equal(a, b)
+    c = fb._accumulate_tail_array(np.copy(in_arr), h_arr, size, 7, 3, 1).copy()
+    assert np.array_equal(a, c)
+
+
+def test_line_kernel_golden(fb):
+    g = load_golden('kat_lines')
+    i = 0
+    while 'in_%d' % i in g:
+        L, T, n, alpha = g['par_%d' % i]
+        L, T, n = int(L), int(T), int(n)
+        out = fb._accumulate_tail_array(g['in_%d' % i].copy(), np.empty(L), L, 2 * T + 1, n, alpha)
+        assert same_up_to_zero_sign(out, g['tail_%d' % i]), 'tail line %d' % i
+        out = fb._accumulate_array(g['in_%d' % i].copy(), np.empty(L), L, 2 * T + 1, n)
+        assert same_up_to_zero_sign(out, g['plain_%d' % i]), 'plain line %d' % i
+        i += 1
+    assert i >= 9
+
+
+def test_line_batches_vs_oracle(fb, orc):
+    """ many lines at once, every fused-pass count, ragged inner sizes (lane masking) """
+    from fastbarnes import _lib
+    rng = np.random.default_rng(7)
+    for (n_outer, L, n_inner, T, n, alpha) in [(3, 97, 37, 5, 4, 0.3), (1, 300, 16, 27, 4, 0.2083), (2, 64, 1, 0, 3, 0.03),
+                                               (1, 130, 50, 13, 6, 0.7), (2, 61, 17, 27, 1, 0.5), (1, 260, 33, 54, 4, 0.926),
+                                               (1, 90, 20, 4, 9, 0.11), (1, 1000, 5, 7, 2, 0.9), (1, 70, 3, 33, 5, 0.4)]:
+        x = rng.normal(size=(n_outer, L, n_inner))
+        x[rng.uniform(size=x.shape) < 0.3] = 0.0
+        y = x.copy()
+        _lib.check(_lib.lib().fb_accumulate_lines_host(_lib.dptr(y), n_outer, L, n_inner, 2 * T + 1, n, alpha))
+        for o in range(n_outer):
+            for i in range(n_inner):
+                line = np.ascontiguousarray(x[o, :, i])
+                ref = orc._accumulate_tail_array(line.copy(), np.empty(L), L, 2 * T + 1, n, alpha)
+                assert same_up_to_zero_sign(y[o, :, i], ref), (n_outer, L, n_inner, T, n, o, i)
+
+
+# ---------------------------------------------------------------------------------------------
+# stages and whole path against the golden fixtures (outputs of the reference itself)
+
+@pytest.mark.parametrize('name', CASES)
+def test_inject_golden(fb, name):
+    g = load_golden(name)
+    size = tuple(int(s) for s in g['size'])
+    vg, wg, offset = fb._inject_data(g['pts'], g['val'], g['x0'] * np.ones(len(size)), g['step'] * np.ones(len(size)), size)
+    assert offset == float(g['offset'])
+    assert bits_equal(vg, g['vin']) and bits_equal(wg, g['win'])
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_convolve_golden(fb, name):
+    g = load_golden(name)
+    size = tuple(int(s) for s in g['size'])
+    dim = len(size)
+    vg, wg = g['vin'].copy(), g['win'].copy()
+    sigma = g['sigma'] * np.ones(dim)
+    step = g['step'] * np.ones(dim)
+    ks = 2 * g['T'] + 1
+    mdw = exp(-float(g['max_dist']) ** 2 / 2)
+    if int(g['plain']):
+        (fb._convolve_1d, fb._convolve_2d, fb._convolve_3d)[dim - 1](vg, wg, sigma, step, size, ks, int(g['num_iter']), mdw)
+    else:
+        (fb._convolve_tail_1d, fb._convolve_tail_2d, fb._convolve_tail_3d)[dim - 1](
+            vg, wg, sigma, step, size, ks, int(g['num_iter']), g['alpha'], mdw)
+    assert same_up_to_zero_sign(vg, g['vg'])
+    assert same_up_to_zero_sign(wg, g['wg'])
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_barnes_golden(fb, name):
+    g = load_golden(name)
+    size = tuple(int(s) for s in g['size'])
+    dim = len(size)
+    pts = g['pts'] if dim > 1 else g['pts'].reshape(-1)
+    sigma = g['sigma'] if len(g['sigma']) > 1 else float(g['sigma'][0])
+    x0 = g['x0'] if len(g['x0']) > 1 else float(g['x0'][0])
+    step = g['step'] if len(g['step']) > 1 else float(g['step'][0])
+    val0 = g['val'].copy()
+    out32, out64 = fb.barnes(pts, g['val'], sigma, x0, step, size if dim > 1 else size[0],
+                             method='convolution' if int(g['plain']) else 'optimized_convolution',
+                             num_iter=int(g['num_iter']), max_dist=float(g['max_dist']), return_float64=True)
+    assert np.array_equal(val0, g['val'])                     # caller's array untouched
+    assert out32.dtype == np.float32 and out32.shape == size[::-1]
+    assert bits_equal(out64, g['out64']), 'fp64 quotient must be bit-identical'
+    assert bits_equal(out32, g['out32']), 'float32 field must be bit-identical'
+    assert np.isnan(out32).mean() > 0.1                       # the mask is exercised
+
+
+def test_paper_case_c1(fb):
+    """ 2400x1200, N=3490, sigma=1, step=1/32, n=4: sha256 of the reference's output. """
+    g = load_golden('c1_paper')
+    size = tuple(int(s) for s in g['size'])
+    out32, out64 = fb.barnes(g['pts'], g['val'], float(g['sigma']), g['x0'], float(g['step']), size,
+                             num_iter=int(g['num_iter']), return_float64=True)
+    assert out32.shape == (1200, 2400)
+    assert bits_equal(out32[::13, ::17], g['sub_out32'])
+    assert bits_equal(out64[::13, ::17], g['sub_out64'])
+    assert sha(out32) == str(g['sha_out32'])
+    assert sha(out64) == str(g['sha_out64'])
+    assert np.isnan(out32).mean() == float(g['nan_frac'])
+    vg, wg, offset = fb._inject_data(g['pts'], g['val'], g['x0'], float(g['step']) * np.ones(2), size)
+    assert offset == float(g['offset'])
+    assert sha(vg) == str(g['sha_vin']) and sha(wg) == str(g['sha_win'])
+
+
+def test_random_cases_vs_oracle(fb, orc):
+    """ seeded inputs at sizes the oracle finishes in seconds; 1D/2D/3D, both methods """
+    rng = np.random.default_rng(99)
+    for dim, size, sig in [(1, (3000,), [2.0]), (2, (333, 217), [1.3, 0.9]), (3, (70, 45, 50), [0.6, 0.5, 0.55]),
+                           (2, (1000, 64), [6.0, 0.3]), (3, (33, 200, 17), [0.35, 2.0, 0.3])]:
+        for n in (1, 2, 3, 4, 5, 6, 7, 10):
+            for method in ('optimized_convolution', 'convolution'):
+                N = 700
+                ext = (np.asarray(size) - 1) * 0.1
+                pts = rng.uniform(-0.05, 0.8, (N, dim)) * ext
+                pts[:100] = pts[100:200]                      # duplicates -> ordered accumulation
+                val = rng.normal(3, 20, N)
+                try:
+                    a = fb.barnes(pts if dim > 1 else pts[:, 0], val, sig, [0.0] * dim, 0.1, size if dim > 1 else size[0],
+                                  method=method, num_iter=n)
+                except RuntimeError as e:
+                    assert 'kernel size' in str(e)
+                    continue
+                b = orc.barnes(pts, val, sig, [0.0] * dim, 0.1, size, method=method, num_iter=n, nthreads=8)
+                assert bits_equal(a, b), (dim, size, n, method)
+
+
+def test_batched_equals_singles(fb):
+    rng = np.random.default_rng(5)
+    size = (160, 120)
+    counts = [300, 1, 57, 800, 300]
+    offs = np.concatenate([[0], np.cumsum(counts)])
+    pts = rng.uniform(0, 1, (offs[-1], 2)) * np.asarray([15.9, 11.9])
+    val = rng.normal(1000, 10, offs[-1])
+    out = fb.barnes_batched(pts, val, 0.8, [0.0, 0.0], 0.1, size, sample_offsets=offs, num_iter=4)
+    assert out.shape == (5, 120, 160)
+    for b in range(5):
+        single = fb.barnes(pts[offs[b]:offs[b + 1]], val[offs[b]:offs[b + 1]], 0.8, [0.0, 0.0], 0.1, size, num_iter=4)
+        assert bits_equal(out[b], single), b
+    # (B, N, M) form
+    p3 = rng.uniform(0, 1, (4, 200, 2)) * np.asarray([15.9, 11.9])
+    v3 = rng.normal(0, 1, (4, 200))
+    out = fb.barnes_batched(p3, v3, 0.8, [0.0, 0.0], 0.1, size)
+    for b in range(4):
+        assert bits_equal(out[b], fb.barnes(p3[b], v3[b], 0.8, [0.0, 0.0], 0.1, size))
+
+
+# ---------------------------------------------------------------------------------------------
+# the reference's integration tests (tests/BasicTest.py), through the drop-in API
+
+def _in_range(arr, lo, hi, eps):
+    return bool(np.all(np.logical_or(np.logical_and(arr >= lo - eps, arr <= hi + eps), np.isnan(arr))))
+
+
+def test_basic_1d(fb):
+    step, size = 1.0 / 64, 129
+    pts = np.asarray([0.15, 0.2, 0.33, 0.35, 0.46, 0.59, 0.61, 0.66, 0.83, 0.98, 1.21, 1.29, 1.4, 1.57, 1.6, 1.79])
+    val = np.asarray([1.0, 0.0, 1.0, 1.0, 0.0, 1.0, 1.0, 0.0, 0.0, 1.0, 0.0, 1.0, 1.0, 1.0, 0.0, 1.0])
+    for method in ['convolution', 'optimized_convolution']:
+        for sigma in [0.5, 0.2, 0.05]:
+            for num_iter in [1, 2, 3, 4, 5, 6, 8, 10]:
+                res = fb.barnes(pts, val, sigma, 0.0, step, size, method=method, num_iter=num_iter)
+                assert _in_range(res, 0.0, 1.0, 1e-15)
+
+
+def test_basic_2d_3d(fb):
+    rng = np.random.default_rng(3)
+    step = 1.0 / 64
+    pts = 2.0 * rng.random((60, 2))
+    val = rng.integers(2, size=60).astype(np.float64)
+    for method in ['convolution', 'optimized_convolution']:
+        for sigma in [0.5, 0.2, 0.05]:
+            for num_iter in [1, 2, 3, 4, 5, 6, 8, 10]:
+                res = fb.barnes(pts, val, sigma, 0.0, step, (129, 129), method=method, num_iter=num_iter)
+                assert _in_range(res, 0.0, 1.0, 5e-13)
+    pts = 2.0 * rng.random((307, 3))
+    val = rng.integers(2, size=307).astype(np.float64)
+    for method in ['convolution', 'optimized_convolution']:
+        for sigma in [0.5, 0.2, 0.05]:
+            for num_iter in [1, 3, 4, 6, 10]:
+                res = fb.barnes(pts, val, sigma, 0.0, step, (129, 129, 129), method=method, num_iter=num_iter)
+                assert _in_range(res, 0.0, 1.0, 1e-12)
+
+
+def test_array_width_vs_kernel_size(fb):
+    sigma, step = 0.5, 1.0 / 32
+    pts = np.asarray([0.2, 0.4, 0.7])
+    val = np.asarray([18.5, 17.0, 19.25])
+    for method, hk in (('convolution', fb.get_half_kernel_size), ('optimized_convolution', fb.get_half_kernel_size_opt)):
+        for num_iter in [3, 4, 6]:
+            kernel_size = 2 * hk(sigma, step, num_iter) + 1
+            fb.barnes(pts, val, sigma, 0.0, step, kernel_size + 1, method=method, num_iter=num_iter)
+            with pytest.raises(RuntimeError):
+                fb.barnes(pts, val, sigma, 0.0, step, kernel_size, method=method, num_iter=num_iter)
+
+
+def test_gaussian_1_dim_opt(fb):
+    """ tests/GaussianApproximationTest.py:66-100 through _convolve_tail_1d """
+    for sigma in [0.6, 0.8, 1.0, 1.5, 2.0]:
+        for (num_iter, max_diff) in [[3, 0.02395], [4, 0.01405], [5, 0.012325], [6, 0.010045]]:
+            delta = 1.0 / 512.0
+            width = 3.5 * sigma
+            grid = np.arange(-width, width + 0.000001, delta)
+            gaussian = 1.0 / sqrt(2.0 * pi) / sigma * np.exp(-(grid / sigma) ** 2 / 2)
+            values = np.zeros(len(grid))
+            values[len(grid) // 2] = 1.0 / delta
+            weights = np.copy(values)
+            np_sigma, np_delta = fb._to_np(sigma), fb._to_np(delta)
+            kernel_size = 2 * fb._get_half_kernel_size_opt(np_sigma, np_delta, num_iter) + 1
+            tail_value = fb._get_tail_value(np_sigma, np_delta, num_iter)
+            fb._convolve_tail_1d(values, weights, np_sigma, np_delta, (len(grid),), kernel_size, num_iter, tail_value, 9999.9)
+            values *= (delta / 2 / sqrt(3 / num_iter) / sigma) ** num_iter
+            assert np.max(np.abs(gaussian - values)) <= max_diff / sigma
+            assert np.all(np.isnan(weights))
+
+
+def test_gaussian_1_dim_plain(fb):
+    """ tests/GaussianApproximationTest.py:32-64 through _convolve_1d """
+    for sigma in [0.6, 1.0, 2.0]:
+        for (num_iter, max_diff) in [[3, 0.02395], [4, 0.01405], [5, 0.01232], [6, 0.01004]]:
+            delta = 1.0 / 512.0
+            width = 3.5 * sigma
+            grid = np.arange(-width, width + 0.000001, delta)
+            sigma_eff = fb.get_sigma_effective(sigma, delta, num_iter)
+            gaussian = 1.0 / sqrt(2.0 * pi) / sigma_eff * np.exp(-(grid / sigma_eff) ** 2 / 2)
+            values = np.zeros(len(grid))
+            values[len(grid) // 2] = 1.0 / delta
+            weights = np.copy(values)
+            np_sigma, np_delta = fb._to_np(sigma), fb._to_np(delta)
+            kernel_size = 2 * fb._get_half_kernel_size(np_sigma, np_delta, num_iter) + 1
+            fb._convolve_1d(values, weights, np_sigma, np_delta, (len(grid),), kernel_size, num_iter, 9999.9)
+            values *= (delta / 2 / sqrt(3 / num_iter) / sigma_eff) ** num_iter
+            assert np.max(np.abs(gaussian - values)) <= max_diff / sigma_eff
+
+
+# ---------------------------------------------------------------------------------------------
+# edge cases and size-independent properties
+
+def test_edge_cases(fb):
+    size = (64, 48)
+    # sample exactly on the last node (xc == size-1) is skipped -> all NaN
+    res = fb.barnes(np.asarray([[7.875, 2.0]]), np.asarray([5.0]), 0.5, [0.0, 0.0], 0.125, size)
+    assert np.all(np.isnan(res))
+    # a single sample gives a constant field wherever defined
+    res = fb.barnes(np.asarray([[3.0, 2.0]]), np.asarray([5.0]), 0.5, [0.0, 0.0], 0.125, size)
+    assert np.all(res[~np.isnan(res)] == 5.0) and (~np.isnan(res)).sum() > 100
+    # out-of-grid samples are ignored
+    a = fb.barnes(np.asarray([[3.0, 2.0], [-1.0, 2.0], [3.0, 99.0]]), np.asarray([5.0, 5.0, 5.0]), 0.5, [0.0, 0.0], 0.125, size)
+    assert bits_equal(a, res)
+    # float32 pts and integer val are converted
+    b = fb.barnes(np.asarray([[3.0, 2.0]], dtype=np.float32), np.asarray([5]), 0.5, [0.0, 0.0], 0.125, size)
+    assert bits_equal(b, res)
+    # N == 0
+    with pytest.raises(ValueError):
+        fb.barnes(np.zeros((0, 2)), np.zeros(0), 0.5, [0.0, 0.0], 0.1, size)
+    # validation errors are RuntimeErrors like in the reference
+    with pytest.raises(RuntimeError):
+        fb.barnes([[1.0, 2.0]], np.asarray([1.0]), 0.5, [0.0, 0.0], 0.1, size)
+    with pytest.raises(RuntimeError):
+        fb.barnes(np.zeros((2, 2)), np.zeros(3), 0.5, [0.0, 0.0], 0.1, size)
+    with pytest.raises(RuntimeError):
+        fb.barnes(np.zeros((2, 2)), np.zeros(2), [0.5, 0.5, 0.5], [0.0, 0.0], 0.1, size)
+    with pytest.raises(RuntimeError):
+        fb.barnes(np.zeros((2, 2)), np.zeros(2), 0.5, [0.0, 0.0], 0.1, size, method='bogus')
+
+
+def test_properties_full_size(fb):
+    """ size-independent properties at the paper grid (2400 x 1200) with 50k random samples """
+    rng = np.random.default_rng(11)
+    size = (2400, 1200)
+    step = 1.0 / 32
+    x0 = np.asarray([-26.0 + step, 34.5])
+    N = 50000
+    pts = x0 + rng.uniform(0, 1, (N, 2)) * np.asarray([(2400 - 1) / 32, (1200 - 1) / 32])
+    val = rng.normal(1000, 10, N)
+    a = fb.barnes(pts, val, 1.0, x0, step, size)
+    # determinism: bit-identical on repetition
+    assert bits_equal(a, fb.barnes(pts, val, 1.0, x0, step, size))
+    # constant observations reproduce the constant exactly
+    c = fb.barnes(pts, np.full(N, 1013.25), 1.0, x0, step, size)
+    assert np.all(c[~np.isnan(c)] == np.float32(1013.25))
+    assert np.array_equal(np.isnan(c), np.isnan(a))
+    # convex combination: min <= field <= max
+    assert np.nanmin(a) >= val.min() - 1e-3 and np.nanmax(a) <= val.max() + 1e-3
+    # affine equivariance with exactly representable scale/shift of the centred values
+    b = fb.barnes(pts, 2.0 * val, 1.0, x0, step, size)
+    assert np.allclose(b[~np.isnan(b)], 2.0 * a[~np.isnan(a)], rtol=3e-7, atol=0)
+
+
+# ---------------------------------------------------------------------------------------------
+# S2 path
+
+S2_RTOL = 2e-6
+
+
+def test_lambert_to_map(fbS2):
+    from fastbarnes.util import lambert_conformal
+    g = load_golden('s2_res8')
+    proj = fbS2.get_lambert_proj()
+    assert np.array_equal(np.asarray(proj), g['proj'])        # host libm: bit-identical
+    lam = lambert_conformal.to_map(g['pts'], g['pts'].copy(), *proj)
+    assert np.max(np.abs(lam - g['lam_pts'])) <= 1e-13        # CUDA math: <= 2 ulp per function
+
+
+@pytest.mark.parametrize('res', [8, 32])
+def test_barnes_s2_golden(fbS2, res):
+    g = load_golden('s2_res%d' % res)
+    size = tuple(int(s) for s in g['size'])
+    step = float(g['step'])
+    out = fbS2.barnes_S2(g['pts'], g['val'], 1.0, g['x0'], step, size, method='optimized_convolution_S2', num_iter=4)
+    lam = fbS2.barnes_S2(g['pts'], g['val'], 1.0, g['x0'], step, size, method='optimized_convolution_S2', num_iter=4,
+                         resample=False)
+    assert out.shape == (size[1], size[0]) and out.dtype == np.float32
+    assert lam.shape == (int(44.0 / step), int(64.0 / step))
+    ref_out = g['out'] if 'out' in g else None
+    if ref_out is not None:
+        assert np.array_equal(np.isnan(out), np.isnan(ref_out))
+        m = ~np.isnan(ref_out)
+        assert np.max(np.abs(out[m] - ref_out[m]) / np.abs(ref_out[m])) <= S2_RTOL
+        assert np.mean(out[m] != ref_out[m]) < 0.01
+        assert np.array_equal(np.isnan(lam), np.isnan(g['lam']))
+        ml = ~np.isnan(g['lam'])
+        assert np.max(np.abs(lam[ml] - g['lam'][ml]) / np.abs(g['lam'][ml])) <= S2_RTOL
+    so, sl = out[::7, ::11], lam[::7, ::11]
+    assert np.array_equal(np.isnan(so), np.isnan(g['sub_out']))
+    m = ~np.isnan(g['sub_out'])
+    assert np.max(np.abs(so[m] - g['sub_out'][m]) / np.abs(g['sub_out'][m])) <= S2_RTOL
+    ml = ~np.isnan(g['sub_lam'])
+    assert np.max(np.abs(sl[ml] - g['sub_lam'][ml]) / np.abs(g['sub_lam'][ml])) <= S2_RTOL
+    # split API (timing5 of the reference) gives the same field as the fused call
+    p1 = fbS2.interpolate_opt_convol_S2_part1(g['pts'], g['val'].copy(), np.full(2, 1.0), g['x0'], np.full(2, step), size,
+                                              4, exp(-3.5 ** 2 / 2))
+    out2 = fbS2.interpolate_opt_convol_S2_part2(*p1)
+    assert bits_equal(out2, out) and bits_equal(p1[0], lam)
+
+
+def test_resample_exact_on_reference_field(fbS2):
+    """ resampling alone, fed with the reference's own Lambert field: the only non-libm inputs are
+    the per-row rho and per-column sin/cos tables """
+    g = load_golden('s2_res8')
+    size = tuple(int(s) for s in g['size'])
+    out = fbS2._resample(g['lam'], np.asarray([-32.0, -2.0]), g['x0'], np.full(2, float(g['step'])), size, *g['proj'])
+    m = ~np.isnan(g['out'])
+    assert np.array_equal(np.isnan(out), np.isnan(g['out']))
+    assert np.max(np.abs(out[m] - g['out'][m]) / np.abs(g['out'][m])) <= S2_RTOL
