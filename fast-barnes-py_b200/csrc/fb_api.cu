@@ -97,47 +97,62 @@ struct AxisParams { int T; double alpha; };
 // ---- sweeps ------------------------------------------------------------------------------------
 constexpr size_t kSmemLimit = 227 * 1024 - 1024;   // opt-in dynamic smem per CTA, minus slack
 
+// chunk length U and ring depth R of a sweep with delay D = 2T+2 (see fb_sweep_kernel)
+inline int sweep_chunk(int D) { return D >= FB_SWEEP_U ? FB_SWEEP_U : FB_SWEEP_U_SMALL; }
+inline int sweep_ring_depth(int D)
+{
+    const int U = sweep_chunk(D);
+    return (D + U + U - 1) / U * U;
+}
+
 size_t sweep_smem_bytes(int npass, int mode, int D)
 {
     const int nr = npass - 1;
-    size_t b = (size_t)nr * D * 32 * sizeof(double);
+    size_t b = (size_t)nr * sweep_ring_depth(D) * 32 * sizeof(double);
     if (mode == 1) b += (size_t)FB_TILE_K * FB_TILE_PITCH * sizeof(double);
     return b;
 }
 
-template <int NPASS, int MODE>
+template <int NPASS, int MODE, int U>
 int launch_sweep_t(const FbSweep &p, size_t smem, cudaStream_t st)
 {
-    static thread_local size_t configured[16] = {0};   // per device would be more exact; attribute is sticky per function
+    static thread_local size_t configured[16] = {0};   // the attribute is sticky per function and device
     int dev = 0;
     cudaGetDevice(&dev);
     if (smem > 48 * 1024 && configured[dev & 15] < smem) {
-        CUDA_TRY(cudaFuncSetAttribute(fb_sweep_kernel<NPASS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        CUDA_TRY(cudaFuncSetAttribute(fb_sweep_kernel<NPASS, MODE, U>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)kSmemLimit));
-        CUDA_TRY(cudaFuncSetAttribute(fb_sweep_kernel<NPASS, MODE>, cudaFuncAttributePreferredSharedMemoryCarveout,
+        CUDA_TRY(cudaFuncSetAttribute(fb_sweep_kernel<NPASS, MODE, U>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                       cudaSharedmemCarveoutMaxShared));
         configured[dev & 15] = kSmemLimit;
     }
     const long long nwarps = p.n_outer * p.n_groups;
     if (nwarps <= 0) return FB_OK;
     if (nwarps > 2147483647LL) return fail(FB_EINVAL, "too many grid lines for one launch: %lld", nwarps);
-    fb_sweep_kernel<NPASS, MODE><<<(unsigned)nwarps, 32, smem, st>>>(p);
+    fb_sweep_kernel<NPASS, MODE, U><<<(unsigned)nwarps, 32, smem, st>>>(p);
     LAUNCH_CHECK();
     return FB_OK;
+}
+
+template <int MODE, int U>
+int launch_sweep_u(int npass, const FbSweep &p, size_t smem, cudaStream_t st)
+{
+    switch (npass) {
+    case 1: return launch_sweep_t<1, MODE, U>(p, smem, st);
+    case 2: return launch_sweep_t<2, MODE, U>(p, smem, st);
+    case 3: return launch_sweep_t<3, MODE, U>(p, smem, st);
+    case 4: return launch_sweep_t<4, MODE, U>(p, smem, st);
+    case 5: return launch_sweep_t<5, MODE, U>(p, smem, st);
+    case 6: return launch_sweep_t<6, MODE, U>(p, smem, st);
+    }
+    return fail(FB_EINVAL, "unsupported number of fused passes: %d", npass);
 }
 
 template <int MODE>
 int launch_sweep_m(int npass, const FbSweep &p, size_t smem, cudaStream_t st)
 {
-    switch (npass) {
-    case 1: return launch_sweep_t<1, MODE>(p, smem, st);
-    case 2: return launch_sweep_t<2, MODE>(p, smem, st);
-    case 3: return launch_sweep_t<3, MODE>(p, smem, st);
-    case 4: return launch_sweep_t<4, MODE>(p, smem, st);
-    case 5: return launch_sweep_t<5, MODE>(p, smem, st);
-    case 6: return launch_sweep_t<6, MODE>(p, smem, st);
-    }
-    return fail(FB_EINVAL, "unsupported number of fused passes: %d", npass);
+    if (sweep_chunk(p.D) == FB_SWEEP_U) return launch_sweep_u<MODE, FB_SWEEP_U>(npass, p, smem, st);
+    return launch_sweep_u<MODE, FB_SWEEP_U_SMALL>(npass, p, smem, st);
 }
 
 // A pair of fp64 grids (value field, weight field) in device memory.
@@ -161,6 +176,7 @@ int run_sweep(int mode, int num_iter, AxisParams ax, Pair &cur, Pair &spare, flo
     p.n_groups = (n_inner + 15) / 16;
     p.T = ax.T;
     p.D = 2 * ax.T + 2;
+    p.R = sweep_ring_depth(p.D);
     p.has_w = has_w ? 1 : 0;
     p.alpha = ax.alpha;
     p.csf = csf;
