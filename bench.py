@@ -291,7 +291,7 @@ def run_gpu(args, rank, local_rank, world):
         try:
             with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as f:
                 tj = json.load(f)
-            traffic = tj.get('sweep_x_bytes_per_launch' if dominant_is_x else 'sweep_y_bytes_per_launch')
+            traffic = tj['sweep_x_bytes_per_point' if dominant_is_x else 'sweep_y_bytes_per_point'] * pts_launch
         except Exception:
             pass
         line = {
