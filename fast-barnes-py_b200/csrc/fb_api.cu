@@ -24,6 +24,7 @@ namespace {
 thread_local std::string g_err;
 std::atomic<long long> g_launches{0};
 std::atomic<int> g_profiling{0};
+std::atomic<int> g_two_warp{1};     // tuning switch (fb_set_option): two-warp sweep kernels on/off
 
 int fail(int code, const char *fmt, ...)
 {
@@ -111,6 +112,58 @@ size_t sweep_smem_bytes(int npass, int mode, int D)
     size_t b = (size_t)nr * sweep_ring_depth(D) * 32 * sizeof(double);
     if (mode == 1) b += (size_t)FB_TILE_K * FB_TILE_PITCH * sizeof(double);
     return b;
+}
+
+// two-warp kernel: split of npass into (NA, NB); B gets the smaller half except that the
+// finalising sweep (MODE 2, expensive division in warp B) gives B a single pass when npass >= 3
+inline int sweep2_na(int npass, int mode) { return (mode == 2 && npass >= 3) ? npass - 1 : (npass + 1) / 2; }
+
+size_t sweep2_smem_bytes(int npass, int mode, int D)
+{
+    const int U = FB_SWEEP_U;
+    const int R = sweep_ring_depth(D);
+    const int R2 = (D + 2 * U + U - 1) / U * U;
+    size_t b = ((size_t)(npass - 2) * R + R2) * 32 * sizeof(double);
+    if (mode == 1) b += (size_t)FB_TILE_K * FB_TILE_PITCH * sizeof(double);
+    return b;
+}
+
+template <int NA, int NB, int MODE>
+int launch_sweep2_t(const FbSweep &p, size_t smem, cudaStream_t st)
+{
+    static thread_local size_t configured[16] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (smem > 48 * 1024 && configured[dev & 15] < smem) {
+        CUDA_TRY(cudaFuncSetAttribute(fb_sweep2_kernel<NA, NB, MODE, FB_SWEEP_U>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)kSmemLimit));
+        CUDA_TRY(cudaFuncSetAttribute(fb_sweep2_kernel<NA, NB, MODE, FB_SWEEP_U>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                      cudaSharedmemCarveoutMaxShared));
+        configured[dev & 15] = kSmemLimit;
+    }
+    const long long nctas = p.n_outer * p.n_groups;
+    if (nctas <= 0) return FB_OK;
+    if (nctas > 2147483647LL) return fail(FB_EINVAL, "too many grid lines for one launch: %lld", nctas);
+    fb_sweep2_kernel<NA, NB, MODE, FB_SWEEP_U><<<(unsigned)nctas, 64, smem, st>>>(p);
+    LAUNCH_CHECK();
+    return FB_OK;
+}
+
+template <int MODE>
+int launch_sweep2_m(int npass, const FbSweep &p, size_t smem, cudaStream_t st)
+{
+    const int na = sweep2_na(npass, MODE);
+    switch (npass * 10 + na) {
+    case 21: return launch_sweep2_t<1, 1, MODE>(p, smem, st);
+    case 32: return launch_sweep2_t<2, 1, MODE>(p, smem, st);
+    case 42: return launch_sweep2_t<2, 2, MODE>(p, smem, st);
+    case 43: return launch_sweep2_t<3, 1, MODE>(p, smem, st);
+    case 53: return launch_sweep2_t<3, 2, MODE>(p, smem, st);
+    case 54: return launch_sweep2_t<4, 1, MODE>(p, smem, st);
+    case 63: return launch_sweep2_t<3, 3, MODE>(p, smem, st);
+    case 65: return launch_sweep2_t<5, 1, MODE>(p, smem, st);
+    }
+    return fail(FB_EINVAL, "unsupported pass split: %d/%d", npass, na);
 }
 
 template <int NPASS, int MODE, int U>
@@ -209,12 +262,22 @@ int run_sweep(int mode, int num_iter, AxisParams ax, Pair &cur, Pair &spare, flo
             p.out_v = spare.v;
             p.out_w = spare.w;
         }
-        const size_t smem = sweep_smem_bytes(np, m, p.D);
-        if (smem > kSmemLimit) return fail(FB_EKERNEL, "ring storage does not fit: T=%d passes=%d", ax.T, np);
         int rc = FB_OK;
-        if (m == 0) rc = launch_sweep_m<0>(np, p, smem, st);
-        else if (m == 1) rc = launch_sweep_m<1>(np, p, smem, st);
-        else rc = launch_sweep_m<2>(np, p, smem, st);
+        // two warps per 16 lines when the launch fuses >= 2 passes (general chunk length only)
+        const bool two_warps = g_two_warp.load() && np >= 2 && sweep_chunk(p.D) == FB_SWEEP_U &&
+                               sweep2_smem_bytes(np, m, p.D) <= kSmemLimit;
+        if (two_warps) {
+            const size_t smem = sweep2_smem_bytes(np, m, p.D);
+            if (m == 0) rc = launch_sweep2_m<0>(np, p, smem, st);
+            else if (m == 1) rc = launch_sweep2_m<1>(np, p, smem, st);
+            else rc = launch_sweep2_m<2>(np, p, smem, st);
+        } else {
+            const size_t smem = sweep_smem_bytes(np, m, p.D);
+            if (smem > kSmemLimit) return fail(FB_EKERNEL, "ring storage does not fit: T=%d passes=%d", ax.T, np);
+            if (m == 0) rc = launch_sweep_m<0>(np, p, smem, st);
+            else if (m == 1) rc = launch_sweep_m<1>(np, p, smem, st);
+            else rc = launch_sweep_m<2>(np, p, smem, st);
+        }
         if (rc != FB_OK) return rc;
         if (m != 2 && !in_place) { Pair t = cur; cur = spare; spare = t; }
     }
@@ -928,6 +991,13 @@ FB_EXPORT int fb_barnes_s2_host(int64_t nsamples, const double *pts, const doubl
 
 // ---- introspection ------------------------------------------------------------------------------------------
 FB_EXPORT int64_t fb_kernel_launch_count(void) { return g_launches.load(); }
+
+FB_EXPORT int fb_set_option(const char *name, int value)
+{
+    if (!name) return fail(FB_EINVAL, "null option name");
+    if (!strcmp(name, "two_warp_sweeps")) { g_two_warp.store(value ? 1 : 0); return FB_OK; }
+    return fail(FB_EINVAL, "unknown option: %s", name);
+}
 
 FB_EXPORT int fb_set_profiling(int enabled)
 {

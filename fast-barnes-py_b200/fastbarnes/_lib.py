@@ -65,6 +65,7 @@ SIGNATURES = {
     'fb_barnes_s2_host': (ctypes.c_int, [ctypes.c_int64, c_double_p, c_double_p, c_double_p, c_double_p,
                                          c_double_p, c_i64_p, ctypes.c_int, ctypes.c_double, c_double_p,
                                          c_float_p]),
+    'fb_set_option': (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int]),
     'fb_kernel_launch_count': (ctypes.c_int64, []),
     'fb_set_profiling': (ctypes.c_int, [ctypes.c_int]),
     'fb_last_profile': (ctypes.c_int, [c_double_p, ctypes.c_int, c_i64_p]),
@@ -102,6 +103,9 @@ def lib():
             fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args
+        # tuning switches from the environment (results are bit-identical either way)
+        if os.environ.get('FB_TWO_WARP_SWEEPS') is not None:
+            L.fb_set_option(b'two_warp_sweeps', int(os.environ['FB_TWO_WARP_SWEEPS']))
         _lib = L
     return _lib
 

@@ -136,6 +136,11 @@ int fb_barnes_s2_host(int64_t nsamples, const double *pts, const double *val, co
                       const double *x0, const double *step, const int64_t *size, int num_iter,
                       double max_dist_weight, const double *proj, float *res);
 
+/* ---- tuning ------------------------------------------------------------------------------- */
+/* process-wide tuning switches that never change results (bit-identical either way):
+ *   "two_warp_sweeps" (default 1): sweep launches that fuse >= 2 passes use two warps per 16 lines */
+int  fb_set_option(const char *name, int value);
+
 /* ---- introspection for benchmarks --------------------------------------------------------- */
 /* number of kernels launched by this library in the calling process so far */
 int64_t fb_kernel_launch_count(void);
