@@ -637,6 +637,31 @@ FB_EXPORT int fb_barnes_dev(const fb_problem *prob, int64_t nsamples, const int6
                     (cudaStream_t)stream, true);
 }
 
+// Host-buffer entry.  Large batches are cut into chunks of fields that run round-robin on a few
+// streams, each with its own workspace slice, so that the H2D copy of chunk i+1, the kernels of
+// chunk i and the D2H copy of chunk i-1 overlap (the float32 output dominates: 4 B per grid point
+// over PCIe).  Chunking never changes results: fields are independent.
+namespace {
+constexpr int kHostStreams = 3;
+cudaStream_t g_host_streams[kHostStreams] = {nullptr, nullptr, nullptr};
+int g_host_streams_device = -1;
+std::atomic<int> g_host_chunk_fields{16};
+
+int host_streams_get()
+{
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (g_host_streams_device != dev) {
+        for (int i = 0; i < kHostStreams; ++i) {
+            if (g_host_streams[i]) cudaStreamDestroy(g_host_streams[i]);
+            CUDA_TRY(cudaStreamCreateWithFlags(&g_host_streams[i], cudaStreamNonBlocking));
+        }
+        g_host_streams_device = dev;
+    }
+    return FB_OK;
+}
+}  // namespace
+
 FB_EXPORT int fb_barnes_host(const fb_problem *prob, int64_t nsamples, const int64_t *sample_offsets,
                              const double *pts, const double *val, float *out, double *out64)
 {
@@ -646,29 +671,79 @@ FB_EXPORT int fb_barnes_host(const fb_problem *prob, int64_t nsamples, const int
     Derived d;
     if ((rc = derive(prob, d)) != FB_OK) return rc;
     if ((rc = check_kernel_vs_grid(prob, d)) != FB_OK) return rc;
+    long long max_n = 0;
+    if ((rc = check_offsets(prob, nsamples, sample_offsets, max_n)) != FB_OK) return rc;
     std::lock_guard<std::mutex> lock(g_arena_mutex);
+
+    // chunking: cf fields per chunk, ns streams
+    const long long nf = prob->nfields;
+    long long cf = g_host_chunk_fields.load();
+    if (cf < 1) cf = 1;
+    const bool chunked = nf >= 2 * cf;
+    if (!chunked) cf = nf;
+    const int ns = chunked ? kHostStreams : 1;
+    const long long nchunks = (nf + cf - 1) / cf;
+
+    // per-slot sizes: worst-case chunk
+    fb_problem cp = *prob;
+    cp.nfields = cf;
+    long long max_chunk_samples = 0;
+    for (long long c = 0; c < nchunks; ++c) {
+        const long long b0 = c * cf, b1 = (b0 + cf < nf) ? b0 + cf : nf;
+        const long long n = sample_offsets ? sample_offsets[b1] - sample_offsets[b0] : (b1 - b0) * max_n;
+        if (n > max_chunk_samples) max_chunk_samples = n;
+    }
     Workspace w;
-    carve(w, nullptr, prob, d.total, nsamples);
-    const size_t npts = (size_t)nsamples * prob->dim, ngrid = (size_t)prob->nfields * d.total;
-    const size_t stage_bytes = align_up(npts * 8) + align_up((size_t)nsamples * 8) + align_up(ngrid * 4) +
-                               (out64 ? align_up(ngrid * 8) : 0) + 1024;
+    carve(w, nullptr, &cp, d.total, max_chunk_samples);
+    const size_t ws_slot = align_up(w.bytes);
+    const size_t cgrid = (size_t)cf * d.total;
+    const size_t stg_slot = align_up((size_t)max_chunk_samples * prob->dim * 8) + align_up((size_t)max_chunk_samples * 8) +
+                            align_up(cgrid * 4) + (out64 ? align_up(cgrid * 8) : 0) + 1024;
     void *ws = nullptr, *stg = nullptr;
-    if ((rc = arena_get(0, w.bytes, &ws)) != FB_OK) return rc;
-    if ((rc = arena_get(1, stage_bytes, &stg)) != FB_OK) return rc;
-    Staging s((char *)stg);
-    double *d_pts = s.take<double>(npts);
-    double *d_val = s.take<double>((size_t)nsamples);
-    float *d_out = s.take<float>(ngrid);
-    double *d_out64 = out64 ? s.take<double>(ngrid) : nullptr;
-    cudaStream_t st = 0;
-    CUDA_TRY(cudaMemcpyAsync(d_pts, pts, npts * 8, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(d_val, val, (size_t)nsamples * 8, cudaMemcpyHostToDevice, st));
-    rc = pipeline(prob, nsamples, sample_offsets, d_pts, d_val, d_out, d_out64, ws, (long long)g_arena[0].bytes, st, true);
-    if (rc != FB_OK) return rc;
-    CUDA_TRY(cudaMemcpyAsync(out, d_out, ngrid * 4, cudaMemcpyDeviceToHost, st));
-    if (out64) CUDA_TRY(cudaMemcpyAsync(out64, d_out64, ngrid * 8, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
-    return FB_OK;
+    if ((rc = arena_get(0, ws_slot * ns, &ws)) != FB_OK) return rc;
+    if ((rc = arena_get(1, stg_slot * ns, &stg)) != FB_OK) return rc;
+    if (chunked && (rc = host_streams_get()) != FB_OK) return rc;
+
+    std::vector<int64_t> rebased;
+    for (long long c = 0; c < nchunks; ++c) {
+        const int slot = (int)(c % ns);
+        cudaStream_t st = chunked ? g_host_streams[slot] : (cudaStream_t)0;
+        const long long b0 = c * cf, b1 = (b0 + cf < nf) ? b0 + cf : nf;
+        const long long s0 = sample_offsets ? sample_offsets[b0] : b0 * max_n;
+        const long long s1 = sample_offsets ? sample_offsets[b1] : b1 * max_n;
+        const long long n = s1 - s0;
+        cp.nfields = b1 - b0;
+        const int64_t *offs = nullptr;
+        if (sample_offsets) {
+            // the pipeline copies the offsets to the device asynchronously: keep every chunk's copy alive
+            const size_t base = rebased.size();
+            if (c == 0) rebased.reserve((size_t)(nf + nchunks));
+            for (long long b = b0; b <= b1; ++b) rebased.push_back(sample_offsets[b] - s0);
+            offs = rebased.data() + base;
+        }
+        Staging s((char *)stg + (size_t)slot * stg_slot);
+        double *d_pts = s.take<double>((size_t)max_chunk_samples * prob->dim);
+        double *d_val = s.take<double>((size_t)max_chunk_samples);
+        float *d_out = s.take<float>(cgrid);
+        double *d_out64 = out64 ? s.take<double>(cgrid) : nullptr;
+        const size_t g = (size_t)(b1 - b0) * d.total;
+        CUDA_TRY(cudaMemcpyAsync(d_pts, pts + (size_t)s0 * prob->dim, (size_t)n * prob->dim * 8, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(d_val, val + s0, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+        rc = pipeline(&cp, n, offs, d_pts, d_val, d_out, d_out64, (char *)ws + (size_t)slot * ws_slot, (long long)ws_slot, st, false);
+        if (rc != FB_OK) break;
+        CUDA_TRY(cudaMemcpyAsync(out + (size_t)b0 * d.total, d_out, g * 4, cudaMemcpyDeviceToHost, st));
+        if (out64) CUDA_TRY(cudaMemcpyAsync(out64 + (size_t)b0 * d.total, d_out64, g * 8, cudaMemcpyDeviceToHost, st));
+    }
+    if (chunked) {
+        for (int i = 0; i < ns; ++i) {
+            cudaError_t e = cudaStreamSynchronize(g_host_streams[i]);
+            if (e != cudaSuccess && rc == FB_OK) rc = fail(FB_ECUDA, "stream sync failed: %s", cudaGetErrorString(e));
+        }
+    } else {
+        cudaError_t e = cudaStreamSynchronize(0);
+        if (e != cudaSuccess && rc == FB_OK) rc = fail(FB_ECUDA, "stream sync failed: %s", cudaGetErrorString(e));
+    }
+    return rc;
 }
 
 // ---- stage entry points -------------------------------------------------------------------------------
@@ -996,6 +1071,7 @@ FB_EXPORT int fb_set_option(const char *name, int value)
 {
     if (!name) return fail(FB_EINVAL, "null option name");
     if (!strcmp(name, "two_warp_sweeps")) { g_two_warp.store(value ? 1 : 0); return FB_OK; }
+    if (!strcmp(name, "host_chunk_fields")) { g_host_chunk_fields.store(value); return FB_OK; }
     return fail(FB_EINVAL, "unknown option: %s", name);
 }
 

@@ -106,6 +106,8 @@ def lib():
         # tuning switches from the environment (results are bit-identical either way)
         if os.environ.get('FB_TWO_WARP_SWEEPS') is not None:
             L.fb_set_option(b'two_warp_sweeps', int(os.environ['FB_TWO_WARP_SWEEPS']))
+        if os.environ.get('FB_HOST_CHUNK_FIELDS') is not None:
+            L.fb_set_option(b'host_chunk_fields', int(os.environ['FB_HOST_CHUNK_FIELDS']))
         _lib = L
     return _lib
 

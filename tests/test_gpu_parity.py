@@ -247,6 +247,38 @@ def test_batched_equals_singles(fb):
         assert bits_equal(out[b], fb.barnes(p3[b], v3[b], 0.8, [0.0, 0.0], 0.1, size))
 
 
+def test_chunked_host_pipeline_and_kernel_variants(fb):
+    """ tuning switches never change bits: multi-stream chunking of the host entry (ragged fields,
+    partial last chunk) and one-warp vs two-warp sweep kernels """
+    from fastbarnes import _lib
+    L = _lib.lib()
+    rng = np.random.default_rng(21)
+    size = (200, 136)
+    counts = [120, 400, 33, 250, 90, 310, 64]
+    offs = np.concatenate([[0], np.cumsum(counts)])
+    pts = rng.uniform(0, 1, (offs[-1], 2)) * np.asarray([19.9, 13.5])
+    pts[:50] = pts[50:100]
+    val = rng.normal(10, 3, offs[-1])
+    ref = fb.barnes_batched(pts, val, 1.2, [0.0, 0.0], 0.1, size, sample_offsets=offs, num_iter=4)
+    try:
+        _lib.check(L.fb_set_option(b'host_chunk_fields', 2))
+        a = fb.barnes_batched(pts, val, 1.2, [0.0, 0.0], 0.1, size, sample_offsets=offs, num_iter=4)
+        p3 = pts[:offs[1]][None].repeat(6, axis=0) + rng.uniform(0, 0.01, (6, counts[0], 1))
+        v3 = rng.normal(0, 1, (6, counts[0]))
+        b = fb.barnes_batched(p3, v3, 1.2, [0.0, 0.0], 0.1, size, num_iter=5)
+        _lib.check(L.fb_set_option(b'host_chunk_fields', 16))
+        b_ref = fb.barnes_batched(p3, v3, 1.2, [0.0, 0.0], 0.1, size, num_iter=5)
+        _lib.check(L.fb_set_option(b'two_warp_sweeps', 0))
+        c = fb.barnes_batched(pts, val, 1.2, [0.0, 0.0], 0.1, size, sample_offsets=offs, num_iter=4)
+    finally:
+        L.fb_set_option(b'host_chunk_fields', 16)
+        L.fb_set_option(b'two_warp_sweeps', 1)
+    assert bits_equal(a, ref) and bits_equal(c, ref) and bits_equal(b, b_ref)
+    for i in range(len(counts)):
+        single = fb.barnes(pts[offs[i]:offs[i + 1]], val[offs[i]:offs[i + 1]], 1.2, [0.0, 0.0], 0.1, size, num_iter=4)
+        assert bits_equal(ref[i], single), i
+
+
 # ---------------------------------------------------------------------------------------------
 # the reference's integration tests (tests/BasicTest.py), through the drop-in API
 
