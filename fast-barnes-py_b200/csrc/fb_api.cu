@@ -116,14 +116,16 @@ size_t sweep_smem_bytes(int npass, int mode, int D)
 
 // two-warp kernel: split of npass into (NA, NB); B gets the smaller half except that the
 // finalising sweep (MODE 2, expensive division in warp B) gives B a single pass when npass >= 3
-inline int sweep2_na(int npass, int mode) { return (mode == 2 && npass >= 3) ? npass - 1 : (npass + 1) / 2; }
+inline int sweep2_na(int npass, int mode) { return mode == 2 ? npass : (npass + 1) / 2; }
 
 size_t sweep2_smem_bytes(int npass, int mode, int D)
 {
     const int U = FB_SWEEP_U;
     const int R = sweep_ring_depth(D);
-    const int R2 = (D + 2 * U + U - 1) / U * U;
-    size_t b = ((size_t)(npass - 2) * R + R2) * 32 * sizeof(double);
+    const int na = sweep2_na(npass, mode), nb = npass - na;
+    const int R2 = nb > 0 ? (D + 2 * U + U - 1) / U * U : 2 * U;
+    const int nrings = (na - 1) + (nb > 0 ? nb - 1 : 0);
+    size_t b = ((size_t)nrings * R + R2) * 32 * sizeof(double);
     if (mode == 1) b += (size_t)FB_TILE_K * FB_TILE_PITCH * sizeof(double);
     return b;
 }
@@ -153,15 +155,23 @@ template <int MODE>
 int launch_sweep2_m(int npass, const FbSweep &p, size_t smem, cudaStream_t st)
 {
     const int na = sweep2_na(npass, MODE);
-    switch (npass * 10 + na) {
-    case 21: return launch_sweep2_t<1, 1, MODE>(p, smem, st);
-    case 32: return launch_sweep2_t<2, 1, MODE>(p, smem, st);
-    case 42: return launch_sweep2_t<2, 2, MODE>(p, smem, st);
-    case 43: return launch_sweep2_t<3, 1, MODE>(p, smem, st);
-    case 53: return launch_sweep2_t<3, 2, MODE>(p, smem, st);
-    case 54: return launch_sweep2_t<4, 1, MODE>(p, smem, st);
-    case 63: return launch_sweep2_t<3, 3, MODE>(p, smem, st);
-    case 65: return launch_sweep2_t<5, 1, MODE>(p, smem, st);
+    if constexpr (MODE == 2) {
+        switch (npass) {
+        case 1: return launch_sweep2_t<1, 0, MODE>(p, smem, st);
+        case 2: return launch_sweep2_t<2, 0, MODE>(p, smem, st);
+        case 3: return launch_sweep2_t<3, 0, MODE>(p, smem, st);
+        case 4: return launch_sweep2_t<4, 0, MODE>(p, smem, st);
+        case 5: return launch_sweep2_t<5, 0, MODE>(p, smem, st);
+        case 6: return launch_sweep2_t<6, 0, MODE>(p, smem, st);
+        }
+    } else {
+        switch (npass * 10 + na) {
+        case 21: return launch_sweep2_t<1, 1, MODE>(p, smem, st);
+        case 32: return launch_sweep2_t<2, 1, MODE>(p, smem, st);
+        case 42: return launch_sweep2_t<2, 2, MODE>(p, smem, st);
+        case 53: return launch_sweep2_t<3, 2, MODE>(p, smem, st);
+        case 63: return launch_sweep2_t<3, 3, MODE>(p, smem, st);
+        }
     }
     return fail(FB_EINVAL, "unsupported pass split: %d/%d", npass, na);
 }
@@ -264,7 +274,7 @@ int run_sweep(int mode, int num_iter, AxisParams ax, Pair &cur, Pair &spare, flo
         }
         int rc = FB_OK;
         // two warps per 16 lines when the launch fuses >= 2 passes (general chunk length only)
-        const bool two_warps = g_two_warp.load() && np >= 2 && sweep_chunk(p.D) == FB_SWEEP_U &&
+        const bool two_warps = g_two_warp.load() && (np >= 2 || m == 2) && sweep_chunk(p.D) == FB_SWEEP_U &&
                                sweep2_smem_bytes(np, m, p.D) <= kSmemLimit;
         if (two_warps) {
             const size_t smem = sweep2_smem_bytes(np, m, p.D);
