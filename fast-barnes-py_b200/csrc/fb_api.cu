@@ -390,15 +390,19 @@ int check_offsets(const fb_problem *pr, long long nsamples, const int64_t *off, 
     return FB_OK;
 }
 
+// z_off / z_cnt: z window of the injected buffers (z-slab runs); the whole grid is (0, d.Dz).
 int run_inject(const fb_problem *pr, const Derived &d, long long nsamples, const int64_t *h_offsets,
-               const double *d_pts, const double *d_val, Workspace &w, cudaStream_t st)
+               const double *d_pts, const double *d_val, Workspace &w, cudaStream_t st,
+               long long z_off = 0, long long z_cnt = -1)
 {
+    if (z_cnt < 0) z_cnt = d.Dz;
+    const long long slab_total = d.W * d.H * z_cnt;
     long long max_n = 0;
     int rc = check_offsets(pr, nsamples, h_offsets, max_n);
     if (rc != FB_OK) return rc;
     if (max_n > 2147483647LL) return fail(FB_EINVAL, "too many samples in one field");
     if ((nsamples << pr->dim) > 4294967295LL) return fail(FB_EINVAL, "too many sample records");
-    const size_t g = (size_t)pr->nfields * (size_t)d.total * sizeof(double);
+    const size_t g = (size_t)pr->nfields * (size_t)slab_total * sizeof(double);
     CUDA_TRY(cudaMemsetAsync(w.vA, 0, g, st));
     CUDA_TRY(cudaMemsetAsync(w.wA, 0, g, st));
     fb_init_kernel<<<(unsigned)((pr->nfields + 255) / 256), 256, 0, st>>>(w.mm, pr->nfields, w.counters);
@@ -421,7 +425,8 @@ int run_inject(const fb_problem *pr, const Derived &d, long long nsamples, const
     if (max_n == 0) return FB_OK;
     FbGrid gr{};
     gr.dim = pr->dim;
-    gr.W = d.W; gr.H = d.H; gr.Dz = d.Dz; gr.total = d.total;
+    gr.W = d.W; gr.H = d.H; gr.Dz = d.Dz; gr.total = slab_total;
+    gr.z_off = z_off; gr.z_cnt = z_cnt;
     for (int m = 0; m < 3; ++m) { gr.x0[m] = pr->x0[m]; gr.step[m] = pr->step[m]; }
 
     const unsigned nf = (unsigned)pr->nfields;
@@ -896,6 +901,153 @@ FB_EXPORT int fb_inject_host(const fb_problem *prob, int64_t nsamples, const int
             offsets[b] = m[2] ? NAN : (dec(m[0]) + dec(m[1])) / 2.0;
         }
     }
+    return FB_OK;
+}
+
+// ---- 3D z-slab decomposition (one slab per GPU) ----------------------------------------------------------
+// A rank owns the planes [z_begin, z_begin + z_count) of the volume and keeps an EXTENDED slab with
+// halo_lo / halo_hi extra planes below / above.  Phase 1 injects into the own planes (records of
+// nodes outside are dropped; every node's ordered sum is complete because all samples are visible)
+// and runs the x and y sweeps, which are independent per plane and therefore bit-identical to the
+// single-GPU run.  The caller then fills the halo planes of the extended B buffers with the
+// neighbours' own planes (NVLink / NCCL send-recv) and phase 2 runs the fused z sweep + finalize
+// over the extended lines.  Each of the n tailed passes reaches T+1 planes, so with
+// halo >= n*(T_z+1) the own planes see every input they depend on; the only difference to the
+// single-GPU run is where the sliding accumulator starts (rounding level).
+namespace {
+struct SlabLayout {
+    double *vA, *wA, *vB, *wB;      // extended slabs: z_ext planes of H*W doubles each
+    float *out_ext;                 // z_ext planes of float32
+    double *out64_ext;
+    Workspace inj;                  // injection scratch (record tables, min/max)
+    size_t off_vB, off_wB;          // byte offsets of the extended B buffers
+    size_t bytes;
+};
+
+int slab_carve(SlabLayout &s, char *base, const fb_problem *pr, const Derived &d, long long nsamples, long long z_ext,
+               bool want64)
+{
+    size_t off = 0;
+    auto take = [&](size_t n) { char *p = base ? base + off : nullptr; off += align_up(n); return p; };
+    const size_t g = (size_t)d.W * d.H * (size_t)z_ext * sizeof(double);
+    s.vA = (double *)take(g);
+    s.wA = (double *)take(g);
+    s.off_vB = off;
+    s.vB = (double *)take(g);
+    s.off_wB = off;
+    s.wB = (double *)take(g);
+    s.out_ext = (float *)take(g / 2);
+    s.out64_ext = want64 ? (double *)take(g) : nullptr;
+    const size_t R = (size_t)nsamples << pr->dim;
+    memset(&s.inj, 0, sizeof s.inj);
+    s.inj.mm = (unsigned long long *)take(FB_MM_STRIDE * 8);
+    s.inj.counters = (unsigned long long *)take(4 * 8);
+    s.inj.offsets = (long long *)take(2 * 8);
+    s.inj.first_mask = (unsigned char *)take((size_t)nsamples + 1);
+    s.inj.rec_k = (int *)take(R * 4 + 4);
+    s.inj.rec_w = (double *)take(R * 8 + 8);
+    s.inj.rec_wv = (double *)take(R * 8 + 8);
+    s.inj.seg_node = (long long *)take(R * 8 + 8);
+    s.inj.seg_base = (unsigned int *)take(R * 4 + 4);
+    s.inj.seg_n = (unsigned int *)take(R * 4 + 4);
+    s.bytes = off;
+    return FB_OK;
+}
+
+int slab_check(const fb_problem *pr, Derived &d, long long z_begin, long long z_count, long long halo_lo, long long halo_hi)
+{
+    int rc = derive(pr, d);
+    if (rc != FB_OK) return rc;
+    if (pr->dim != 3 || pr->nfields != 1) return fail(FB_EINVAL, "z-slab runs need dim == 3 and nfields == 1");
+    if (z_begin < 0 || z_count < 1 || z_begin + z_count > d.Dz || halo_lo < 0 || halo_hi < 0 ||
+        z_begin - halo_lo < 0 || z_begin + z_count + halo_hi > d.Dz)
+        return fail(FB_EINVAL, "invalid slab: planes [%lld, %lld) halo %lld / %lld of %lld", z_begin, z_begin + z_count,
+                    halo_lo, halo_hi, d.Dz);
+    return FB_OK;
+}
+}  // namespace
+
+FB_EXPORT int64_t fb_slab_halo_planes(const fb_problem *prob)
+{
+    Derived d;
+    if (derive(prob, d) != FB_OK) return FB_EINVAL;
+    if (prob->dim != 3) return fail(FB_EINVAL, "z-slab runs need dim == 3");
+    return (int64_t)prob->num_iter * (d.ax[2].T + 1);
+}
+
+FB_EXPORT int fb_slab_layout(const fb_problem *prob, int64_t nsamples, int64_t z_count, int64_t halo_lo, int64_t halo_hi,
+                             int want_out64, int64_t *workspace_bytes, int64_t *offset_vB, int64_t *offset_wB)
+{
+    Derived d;
+    int rc = derive(prob, d);
+    if (rc != FB_OK) return rc;
+    if (prob->dim != 3 || prob->nfields != 1) return fail(FB_EINVAL, "z-slab runs need dim == 3 and nfields == 1");
+    SlabLayout s;
+    slab_carve(s, nullptr, prob, d, nsamples, z_count + halo_lo + halo_hi, want_out64 != 0);
+    if (workspace_bytes) *workspace_bytes = (int64_t)s.bytes;
+    if (offset_vB) *offset_vB = (int64_t)s.off_vB;
+    if (offset_wB) *offset_wB = (int64_t)s.off_wB;
+    return FB_OK;
+}
+
+FB_EXPORT int fb_slab_phase1_dev(const fb_problem *prob, int64_t z_begin, int64_t z_count, int64_t halo_lo, int64_t halo_hi,
+                                 int64_t nsamples, const double *d_pts, const double *d_val, int want_out64,
+                                 void *d_workspace, int64_t workspace_bytes, void *stream)
+{
+    int rc = require_device();
+    if (rc != FB_OK) return rc;
+    Derived d;
+    if ((rc = slab_check(prob, d, z_begin, z_count, halo_lo, halo_hi)) != FB_OK) return rc;
+    if ((rc = check_kernel_vs_grid(prob, d)) != FB_OK) return rc;
+    if (!d_pts || !d_val || !d_workspace) return fail(FB_EINVAL, "null device pointer");
+    const long long z_ext = z_count + halo_lo + halo_hi;
+    SlabLayout s;
+    slab_carve(s, (char *)d_workspace, prob, d, nsamples, z_ext, want_out64 != 0);
+    if ((long long)s.bytes > workspace_bytes) return fail(FB_ENOMEM, "workspace too small: need %zu bytes", s.bytes);
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long plane = d.W * d.H;
+    // injection into the own planes, held in the middle of the extended A buffers
+    Workspace w = s.inj;
+    w.vA = s.vA + halo_lo * plane;
+    w.wA = s.wA + halo_lo * plane;
+    w.vB = s.vB + halo_lo * plane;
+    w.wB = s.wB + halo_lo * plane;
+    if ((rc = run_inject(prob, d, nsamples, nullptr, d_pts, d_val, w, st, z_begin, z_count)) != FB_OK) return rc;
+    // x sweep (A -> B, transposing) and y sweep (in place) on the own planes
+    Pair cur{w.vA, w.wA}, spare{w.vB, w.wB};
+    rc = run_sweep(1, prob->num_iter, d.ax[0], cur, spare, nullptr, nullptr, w.mm, d.csf, z_count, d.W, d.H, true, st);
+    if (rc != FB_OK) return rc;
+    rc = run_sweep(0, prob->num_iter, d.ax[1], cur, spare, nullptr, nullptr, w.mm, d.csf, z_count, d.H, d.W, true, st);
+    if (rc != FB_OK) return rc;
+    if (cur.v != w.vB) {   // per-pass ping-pong may end in the other pair: bring the result home
+        CUDA_TRY(cudaMemcpyAsync(w.vB, cur.v, (size_t)plane * z_count * 8, cudaMemcpyDeviceToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(w.wB, cur.w, (size_t)plane * z_count * 8, cudaMemcpyDeviceToDevice, st));
+    }
+    return FB_OK;
+}
+
+FB_EXPORT int fb_slab_phase2_dev(const fb_problem *prob, int64_t z_begin, int64_t z_count, int64_t halo_lo, int64_t halo_hi,
+                                 int64_t nsamples, float *d_out, double *d_out64, void *d_workspace,
+                                 int64_t workspace_bytes, void *stream)
+{
+    int rc = require_device();
+    if (rc != FB_OK) return rc;
+    Derived d;
+    if ((rc = slab_check(prob, d, z_begin, z_count, halo_lo, halo_hi)) != FB_OK) return rc;
+    if (!d_out || !d_workspace) return fail(FB_EINVAL, "null device pointer");
+    const long long z_ext = z_count + halo_lo + halo_hi;
+    SlabLayout s;
+    slab_carve(s, (char *)d_workspace, prob, d, nsamples, z_ext, d_out64 != nullptr);
+    if ((long long)s.bytes > workspace_bytes) return fail(FB_ENOMEM, "workspace too small: need %zu bytes", s.bytes);
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long plane = d.W * d.H;
+    // fused z sweep + mask + divide + cast over the extended lines (A is free again: spare)
+    Pair cur{s.vB, s.wB}, spare{s.vA, s.wA};
+    rc = run_sweep(2, prob->num_iter, d.ax[2], cur, spare, s.out_ext, s.out64_ext, s.inj.mm, d.csf, 1, z_ext, plane, true, st);
+    if (rc != FB_OK) return rc;
+    CUDA_TRY(cudaMemcpyAsync(d_out, s.out_ext + halo_lo * plane, (size_t)plane * z_count * 4, cudaMemcpyDeviceToDevice, st));
+    if (d_out64)
+        CUDA_TRY(cudaMemcpyAsync(d_out64, s.out64_ext + halo_lo * plane, (size_t)plane * z_count * 8, cudaMemcpyDeviceToDevice, st));
     return FB_OK;
 }
 

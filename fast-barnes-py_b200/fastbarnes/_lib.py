@@ -50,6 +50,15 @@ SIGNATURES = {
     'fb_barnes_dev': (ctypes.c_int, [ctypes.POINTER(FbProblem), ctypes.c_int64, c_i64_p, ctypes.c_void_p,
                                      ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                      ctypes.c_int64, ctypes.c_void_p]),
+    'fb_slab_halo_planes': (ctypes.c_int64, [ctypes.POINTER(FbProblem)]),
+    'fb_slab_layout': (ctypes.c_int, [ctypes.POINTER(FbProblem), ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
+                                      ctypes.c_int64, ctypes.c_int, c_i64_p, c_i64_p, c_i64_p]),
+    'fb_slab_phase1_dev': (ctypes.c_int, [ctypes.POINTER(FbProblem), ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
+                                          ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                          ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]),
+    'fb_slab_phase2_dev': (ctypes.c_int, [ctypes.POINTER(FbProblem), ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
+                                          ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                          ctypes.c_int64, ctypes.c_void_p]),
     'fb_accumulate_lines_host': (ctypes.c_int, [c_double_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
                                                 ctypes.c_int64, ctypes.c_int, ctypes.c_double]),
     'fb_convolve_host': (ctypes.c_int, [ctypes.c_int, c_double_p, c_double_p, c_i64_p, c_i32_p, ctypes.c_int,

@@ -78,3 +78,156 @@ def barnes_batched_sharded(pts, val, sigma, x0, step, size, sample_offsets, meth
         if e > b:
             out[b:e] = parts[r][:e - b].cpu().numpy()
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# 3D volumes: z-slab decomposition with halo exchange
+
+class BarnesSlab3D:
+    """
+    3D optimized-convolution Barnes interpolation of ONE large volume split into z-slabs, one per
+    rank (one process per GPU).  Every rank sees all samples (they are small next to the volume),
+    injects and x/y-sweeps only its own planes -- bit-identical to the single-GPU planes, since
+    those sweeps are independent per plane -- then receives `halo = num_iter*(T_z+1)` planes from
+    each neighbour (torch.distributed send/recv: NCCL over NVLink on GPUs) and runs the fused
+    z sweep + mask + divide + cast over its extended lines.  Within the halo every input an own
+    plane depends on is present; the result differs from the single-GPU run only by where the
+    sliding accumulator starts (rounding level, ~1e-15 relative in the fp64 quotient).
+
+    `nslabs`/`slab` may be given explicitly to run several slabs one after the other in a single
+    process (used by the tests to check the decomposition on one GPU).
+    """
+
+    def __init__(self, sigma, x0, step, size, nsamples, method='optimized_convolution', num_iter=4, max_dist=3.5,
+                 group=None, device=None, want_float64=False, nslabs=None, slab=None):
+        import torch
+        import torch.distributed as dist
+        from . import _lib
+        from .interpolation import _per_axis, _grid_size, _problem, _check_kernel_vs_grid, _CONV_METHODS
+        from math import exp
+        if method not in _CONV_METHODS:
+            raise RuntimeError("encountered invalid Barnes interpolation method: " + str(method))
+        if not torch.cuda.is_available():
+            raise RuntimeError('no CUDA device available; this package has no CPU fallback')
+        self.torch, self.dist, self._lib = torch, dist, _lib
+        self.group = group
+        active = dist.is_available() and dist.is_initialized()
+        self.world = int(nslabs) if nslabs is not None else (dist.get_world_size(group) if active else 1)
+        self.rank = int(slab) if slab is not None else (dist.get_rank(group) if active else 0)
+        self.use_dist = active and nslabs is None and self.world > 1
+        sigma = _per_axis('sigma', sigma, 3)
+        x0 = _per_axis('x0', x0, 3)
+        step = _per_axis('step', step, 3)
+        self.size = _grid_size(size, 3)
+        _check_kernel_vs_grid(method, sigma, step, self.size, num_iter)
+        self.prob = _problem(3, sigma, x0, step, self.size, _CONV_METHODS[method], num_iter, exp(-max_dist ** 2 / 2), 1)
+        L = _lib.lib()
+        self.halo = int(L.fb_slab_halo_planes(self.prob))
+        self.nsamples = int(nsamples)
+        Dz = self.size[2]
+        self.z0, self.z1 = shard_range(Dz, self.world, self.rank)
+        if self.world > 1 and min(shard_range(Dz, self.world, r)[1] - shard_range(Dz, self.world, r)[0]
+                                  for r in range(self.world)) < self.halo:
+            raise RuntimeError('slabs of %d planes are thinner than the halo of %d planes: use fewer ranks'
+                               % (Dz // self.world, self.halo))
+        self.halo_lo = self.halo if self.rank > 0 else 0
+        self.halo_hi = self.halo if self.rank < self.world - 1 else 0
+        self.zc = self.z1 - self.z0
+        self.z_ext = self.zc + self.halo_lo + self.halo_hi
+        nb = _lib.ctypes.c_int64()
+        ov = _lib.ctypes.c_int64()
+        ow = _lib.ctypes.c_int64()
+        _lib.check(L.fb_slab_layout(self.prob, self.nsamples, self.zc, self.halo_lo, self.halo_hi, int(want_float64),
+                                    _lib.ctypes.byref(nb), _lib.ctypes.byref(ov), _lib.ctypes.byref(ow)))
+        self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+        W, H = self.size[0], self.size[1]
+        with torch.cuda.device(self.device):
+            self.workspace = torch.empty(nb.value, dtype=torch.uint8, device=self.device)
+            nbytes = self.z_ext * H * W * 8
+            self.vB = self.workspace[ov.value:ov.value + nbytes].view(torch.float64).view(self.z_ext, H, W)
+            self.wB = self.workspace[ow.value:ow.value + nbytes].view(torch.float64).view(self.z_ext, H, W)
+            self.out = torch.empty((self.zc, H, W), dtype=torch.float32, device=self.device)
+            self.out64 = torch.empty((self.zc, H, W), dtype=torch.float64, device=self.device) if want_float64 else None
+        self.want64 = bool(want_float64)
+
+    # -- the three steps ------------------------------------------------------------------------
+    def phase1(self, pts, val):
+        torch, L, _lib = self.torch, self._lib.lib(), self._lib
+        if pts.dtype != torch.float64 or val.dtype != torch.float64 or not pts.is_cuda or not val.is_cuda:
+            raise RuntimeError('pts and val must be float64 CUDA tensors')
+        with torch.cuda.device(self.device):
+            st = torch.cuda.current_stream().cuda_stream
+            _lib.check(L.fb_slab_phase1_dev(self.prob, self.z0, self.zc, self.halo_lo, self.halo_hi, self.nsamples,
+                                            pts.data_ptr(), val.data_ptr(), int(self.want64),
+                                            self.workspace.data_ptr(), self.workspace.numel(), st))
+
+    def own_planes(self):
+        """ (values, weights) views of the own planes inside the extended slab. """
+        a, b = self.halo_lo, self.halo_lo + self.zc
+        return self.vB[a:b], self.wB[a:b]
+
+    def exchange(self):
+        """ halo exchange with the neighbouring ranks (torch.distributed point-to-point). """
+        if not self.use_dist:
+            return
+        dist, h = self.dist, self.halo
+        v, w = self.own_planes()
+        ops = []
+        if self.rank > 0:                                   # lower neighbour
+            for own, ext in ((v, self.vB), (w, self.wB)):
+                ops.append(dist.P2POp(dist.isend, own[:h].contiguous(), self.rank - 1, self.group))
+                ops.append(dist.P2POp(dist.irecv, ext[:h], self.rank - 1, self.group))
+        if self.rank < self.world - 1:                      # upper neighbour
+            for own, ext in ((v, self.vB), (w, self.wB)):
+                ops.append(dist.P2POp(dist.isend, own[-h:].contiguous(), self.rank + 1, self.group))
+                ops.append(dist.P2POp(dist.irecv, ext[self.halo_lo + self.zc:], self.rank + 1, self.group))
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+
+    def phase2(self):
+        torch, L, _lib = self.torch, self._lib.lib(), self._lib
+        with torch.cuda.device(self.device):
+            st = torch.cuda.current_stream().cuda_stream
+            _lib.check(L.fb_slab_phase2_dev(self.prob, self.z0, self.zc, self.halo_lo, self.halo_hi, self.nsamples,
+                                            self.out.data_ptr(), None if self.out64 is None else self.out64.data_ptr(),
+                                            self.workspace.data_ptr(), self.workspace.numel(), st))
+        return self.out
+
+    def __call__(self, pts, val):
+        """ pts (N, 3), val (N,) float64 CUDA tensors holding ALL samples; returns the rank's planes
+        [z0, z1) as a float32 CUDA tensor (z1 - z0, H, W). """
+        self.phase1(pts, val)
+        self.exchange()
+        return self.phase2()
+
+
+def barnes_slabs_emulated(pts, val, sigma, x0, step, size, nslabs, num_iter=4, max_dist=3.5,
+                          method='optimized_convolution', want_float64=False):
+    """
+    Runs the z-slab decomposition with `nslabs` slabs one after the other on the current GPU,
+    copying the halo planes between the slabs' buffers (what the NCCL exchange does between ranks).
+    Returns the assembled float32 volume (and the fp64 quotient if requested) as numpy arrays.
+    """
+    import torch
+    dp = torch.from_numpy(np.ascontiguousarray(pts, dtype=np.float64)).cuda()
+    dv = torch.from_numpy(np.ascontiguousarray(val, dtype=np.float64)).cuda()
+    slabs = [BarnesSlab3D(sigma, x0, step, size, len(val), method=method, num_iter=num_iter, max_dist=max_dist,
+                          want_float64=want_float64, nslabs=nslabs, slab=r) for r in range(nslabs)]
+    for s in slabs:
+        s.phase1(dp, dv)
+    for r, s in enumerate(slabs):
+        h = s.halo
+        if r > 0:
+            pv, pw = slabs[r - 1].own_planes()
+            s.vB[:h].copy_(pv[-h:])
+            s.wB[:h].copy_(pw[-h:])
+        if r < nslabs - 1:
+            nv, nw = slabs[r + 1].own_planes()
+            s.vB[s.halo_lo + s.zc:].copy_(nv[:h])
+            s.wB[s.halo_lo + s.zc:].copy_(nw[:h])
+    outs = [s.phase2() for s in slabs]
+    torch.cuda.synchronize()
+    vol = torch.cat(outs, dim=0).cpu().numpy()
+    if want_float64:
+        return vol, torch.cat([s.out64 for s in slabs], dim=0).cpu().numpy()
+    return vol

@@ -97,6 +97,25 @@ int fb_barnes_dev(const fb_problem *prob, int64_t nsamples, const int64_t *sampl
                   const double *d_pts, const double *d_val, float *d_out, double *d_out64,
                   void *d_workspace, int64_t workspace_bytes, void *stream);
 
+/* ---- 3D z-slab decomposition (multi-GPU; no counterpart in the single-threaded reference) ---- */
+/* Halo planes a slab needs on each interior side: num_iter * (T_z + 1). */
+int64_t fb_slab_halo_planes(const fb_problem *prob);
+/* Workspace size of a slab of z_count own planes with halo_lo / halo_hi halo planes, and the byte
+ * offsets of its extended B buffers (values, weights; [z_ext][y][x] float64) inside the workspace:
+ * the caller writes the neighbours' planes into the halo parts between phase 1 and phase 2. */
+int fb_slab_layout(const fb_problem *prob, int64_t nsamples, int64_t z_count, int64_t halo_lo, int64_t halo_hi,
+                   int want_out64, int64_t *workspace_bytes, int64_t *offset_vB, int64_t *offset_wB);
+/* Phase 1: centre (over ALL samples) + inject + x sweep + y sweep for the own planes
+ * [z_begin, z_begin + z_count) of the volume described by prob (dim 3, nfields 1). */
+int fb_slab_phase1_dev(const fb_problem *prob, int64_t z_begin, int64_t z_count, int64_t halo_lo, int64_t halo_hi,
+                       int64_t nsamples, const double *d_pts, const double *d_val, int want_out64,
+                       void *d_workspace, int64_t workspace_bytes, void *stream);
+/* Phase 2 (after the halo planes have been filled): z sweep + mask + divide + cast;
+ * d_out [z_count][y][x] float32 receives the own planes. */
+int fb_slab_phase2_dev(const fb_problem *prob, int64_t z_begin, int64_t z_count, int64_t halo_lo, int64_t halo_hi,
+                       int64_t nsamples, float *d_out, double *d_out64, void *d_workspace,
+                       int64_t workspace_bytes, void *stream);
+
 /* ---- stages (private-but-tested functions of the reference) -------------------------------- */
 /* interpolation.py:485-533 _accumulate_tail_array (alpha) / :729-772 _accumulate_array
  * (alpha = 0) applied in place to n_outer*n_inner independent lines of length len stored as
