@@ -98,6 +98,25 @@ struct AxisParams { int T; double alpha; };
 // ---- sweeps ------------------------------------------------------------------------------------
 constexpr size_t kSmemLimit = 227 * 1024 - 1024;   // opt-in dynamic smem per CTA, minus slack
 
+int sm_count(int dev)
+{
+    static int cached[16] = {0};
+    if (cached[dev & 15] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1) n = 148;
+        cached[dev & 15] = n;
+    }
+    return cached[dev & 15];
+}
+
+// Work counters of the persistent sweep launches: one slot per launch of a call, zeroed on the
+// stream right before the launch.
+struct SweepCounters {
+    unsigned long long *base;   // device array of kSweepCounterSlots entries
+    int next;
+};
+constexpr int kSweepCounterSlots = 12;
+
 // chunk length U and ring depth R of a sweep with delay D = 2T+2 (see fb_sweep_kernel)
 inline int sweep_chunk(int D) { return D >= FB_SWEEP_U ? FB_SWEEP_U : FB_SWEEP_U_SMALL; }
 inline int sweep_ring_depth(int D)
@@ -143,10 +162,20 @@ int launch_sweep2_t(const FbSweep &p, size_t smem, cudaStream_t st)
                                       cudaSharedmemCarveoutMaxShared));
         configured[dev & 15] = kSmemLimit;
     }
-    const long long nctas = p.n_outer * p.n_groups;
-    if (nctas <= 0) return FB_OK;
-    if (nctas > 2147483647LL) return fail(FB_EINVAL, "too many grid lines for one launch: %lld", nctas);
-    fb_sweep2_kernel<NA, NB, MODE, FB_SWEEP_U><<<(unsigned)nctas, 64, smem, st>>>(p);
+    const long long nitems = p.n_outer * p.n_groups;
+    if (nitems <= 0) return FB_OK;
+    static thread_local int occ[16] = {0};
+    static thread_local size_t occ_smem[16] = {0};
+    if (occ[dev & 15] == 0 || occ_smem[dev & 15] != smem) {
+        int nb = 0;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fb_sweep2_kernel<NA, NB, MODE, FB_SWEEP_U>, 64, smem));
+        occ[dev & 15] = nb > 0 ? nb : 1;
+        occ_smem[dev & 15] = smem;
+    }
+    long long grid = (long long)occ[dev & 15] * sm_count(dev);
+    if (grid > nitems) grid = nitems;
+    CUDA_TRY(cudaMemsetAsync(p.work_counter, 0, sizeof(unsigned long long), st));
+    fb_sweep2_kernel<NA, NB, MODE, FB_SWEEP_U><<<(unsigned)grid, 64, smem, st>>>(p);
     LAUNCH_CHECK();
     return FB_OK;
 }
@@ -189,10 +218,20 @@ int launch_sweep_t(const FbSweep &p, size_t smem, cudaStream_t st)
                                       cudaSharedmemCarveoutMaxShared));
         configured[dev & 15] = kSmemLimit;
     }
-    const long long nwarps = p.n_outer * p.n_groups;
-    if (nwarps <= 0) return FB_OK;
-    if (nwarps > 2147483647LL) return fail(FB_EINVAL, "too many grid lines for one launch: %lld", nwarps);
-    fb_sweep_kernel<NPASS, MODE, U><<<(unsigned)nwarps, 32, smem, st>>>(p);
+    const long long nitems = p.n_outer * p.n_groups;
+    if (nitems <= 0) return FB_OK;
+    static thread_local int occ[16] = {0};
+    static thread_local size_t occ_smem[16] = {0};
+    if (occ[dev & 15] == 0 || occ_smem[dev & 15] != smem) {
+        int nb = 0;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fb_sweep_kernel<NPASS, MODE, U>, 32, smem));
+        occ[dev & 15] = nb > 0 ? nb : 1;
+        occ_smem[dev & 15] = smem;
+    }
+    long long grid = (long long)occ[dev & 15] * sm_count(dev);
+    if (grid > nitems) grid = nitems;
+    CUDA_TRY(cudaMemsetAsync(p.work_counter, 0, sizeof(unsigned long long), st));
+    fb_sweep_kernel<NPASS, MODE, U><<<(unsigned)grid, 32, smem, st>>>(p);
     LAUNCH_CHECK();
     return FB_OK;
 }
@@ -230,7 +269,7 @@ struct Pair { double *v, *w; };
 // of the two pairs swap.  On return `cur` holds the result (modes 0 and 1).
 int run_sweep(int mode, int num_iter, AxisParams ax, Pair &cur, Pair &spare, float *out32, double *out64,
               const unsigned long long *mm, double csf, long long n_outer, long long L, long long n_inner,
-              bool has_w, cudaStream_t st)
+              bool has_w, cudaStream_t st, SweepCounters &ctr)
 {
     FbSweep p{};
     p.n_outer = n_outer;
@@ -260,6 +299,7 @@ int run_sweep(int mode, int num_iter, AxisParams ax, Pair &cur, Pair &spare, flo
         const bool last = (l == nlaunch - 1);
         const int m = last ? mode : 0;
         const bool in_place = (m == 0 && np >= 2);
+        p.work_counter = ctr.base + (ctr.next++ % kSweepCounterSlots);
         p.in_v = cur.v;
         p.in_w = cur.w;
         if (m == 2) {
@@ -359,7 +399,7 @@ void carve(Workspace &w, char *base, const fb_problem *pr, long long total, long
     w.vB = (double *)take(g);
     w.wB = (double *)take(g);
     w.mm = (unsigned long long *)take((size_t)pr->nfields * FB_MM_STRIDE * 8);
-    w.counters = (unsigned long long *)take(4 * 8);
+    w.counters = (unsigned long long *)take((4 + kSweepCounterSlots) * 8);
     w.offsets = (long long *)take((size_t)(pr->nfields + 1) * 8);
     w.first_mask = (unsigned char *)take((size_t)nsamples + 1);
     w.rec_k = (int *)take(R * 4 + 4);
@@ -455,25 +495,26 @@ int run_sweeps(const fb_problem *pr, const Derived &d, Workspace &w, float *d_ou
     const long long nf = pr->nfields;
     const int n = pr->num_iter;
     Pair cur{w.vA, w.wA}, spare{w.vB, w.wB};
+    SweepCounters ctr{w.counters + 4, 0};
     int rc;
     if (pr->dim == 1) {
-        rc = run_sweep(2, n, d.ax[0], cur, spare, d_out, d_out64, w.mm, d.csf, nf, d.W, 1, true, st);
+        rc = run_sweep(2, n, d.ax[0], cur, spare, d_out, d_out64, w.mm, d.csf, nf, d.W, 1, true, st, ctr);
         if (rc != FB_OK) return rc;
         return prof_mark(3, st);
     }
     // x sweep: A layout [..][x][y] -> natural layout [..][y][x]
-    rc = run_sweep(1, n, d.ax[0], cur, spare, nullptr, nullptr, w.mm, d.csf, nf * d.Dz, d.W, d.H, true, st);
+    rc = run_sweep(1, n, d.ax[0], cur, spare, nullptr, nullptr, w.mm, d.csf, nf * d.Dz, d.W, d.H, true, st, ctr);
     if (rc != FB_OK) return rc;
     if ((rc = prof_mark(3, st)) != FB_OK) return rc;
     if (pr->dim == 2) {
-        rc = run_sweep(2, n, d.ax[1], cur, spare, d_out, d_out64, w.mm, d.csf, nf, d.H, d.W, true, st);
+        rc = run_sweep(2, n, d.ax[1], cur, spare, d_out, d_out64, w.mm, d.csf, nf, d.H, d.W, true, st, ctr);
         if (rc != FB_OK) return rc;
         return prof_mark(4, st);
     }
-    rc = run_sweep(0, n, d.ax[1], cur, spare, nullptr, nullptr, w.mm, d.csf, nf * d.Dz, d.H, d.W, true, st);
+    rc = run_sweep(0, n, d.ax[1], cur, spare, nullptr, nullptr, w.mm, d.csf, nf * d.Dz, d.H, d.W, true, st, ctr);
     if (rc != FB_OK) return rc;
     if ((rc = prof_mark(4, st)) != FB_OK) return rc;
-    rc = run_sweep(2, n, d.ax[2], cur, spare, d_out, d_out64, w.mm, d.csf, nf, d.Dz, d.H * d.W, true, st);
+    rc = run_sweep(2, n, d.ax[2], cur, spare, d_out, d_out64, w.mm, d.csf, nf, d.Dz, d.H * d.W, true, st, ctr);
     if (rc != FB_OK) return rc;
     return prof_mark(5, st);
 }
@@ -762,6 +803,20 @@ FB_EXPORT int fb_barnes_host(const fb_problem *prob, int64_t nsamples, const int
 }
 
 // ---- stage entry points -------------------------------------------------------------------------------
+namespace {
+// work counters for the stage entry points (they have no workspace; serialised by g_arena_mutex, stream 0)
+int stage_counters(SweepCounters &ctr)
+{
+    static unsigned long long *buf[16] = {nullptr};
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (!buf[dev & 15]) CUDA_TRY(cudaMalloc(&buf[dev & 15], kSweepCounterSlots * sizeof(unsigned long long)));
+    ctr.base = buf[dev & 15];
+    ctr.next = 0;
+    return FB_OK;
+}
+}  // namespace
+
 FB_EXPORT int fb_accumulate_lines_host(double *lines, int64_t n_outer, int64_t len, int64_t n_inner,
                                        int64_t rect_len, int num_iter, double alpha)
 {
@@ -778,7 +833,9 @@ FB_EXPORT int fb_accumulate_lines_host(double *lines, int64_t n_outer, int64_t l
     cudaStream_t st = 0;
     CUDA_TRY(cudaMemcpyAsync(cur.v, lines, n * 8, cudaMemcpyHostToDevice, st));
     AxisParams ax{(int)((rect_len - 1) / 2), alpha};
-    rc = run_sweep(0, num_iter, ax, cur, spare, nullptr, nullptr, nullptr, 0.0, n_outer, len, n_inner, false, st);
+    SweepCounters ctr{nullptr, 0};
+    if ((rc = stage_counters(ctr)) != FB_OK) return rc;
+    rc = run_sweep(0, num_iter, ax, cur, spare, nullptr, nullptr, nullptr, 0.0, n_outer, len, n_inner, false, st, ctr);
     if (rc != FB_OK) return rc;
     CUDA_TRY(cudaMemcpyAsync(lines, cur.v, n * 8, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
@@ -823,8 +880,10 @@ FB_EXPORT int fb_convolve_host(int dim, double *vg, double *wg, const int64_t *s
     CUDA_TRY(cudaMemcpyAsync(v0, vg, n * 8, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(w0, wg, n * 8, cudaMemcpyHostToDevice, st));
     Pair cur{v0, w0}, spare{v1, w1};
+    SweepCounters ctr{nullptr, 0};
+    if ((rc = stage_counters(ctr)) != FB_OK) return rc;
     if (dim == 1) {
-        rc = run_sweep(0, num_iter, ax[0], cur, spare, nullptr, nullptr, nullptr, 0.0, 1, W, 1, true, st);
+        rc = run_sweep(0, num_iter, ax[0], cur, spare, nullptr, nullptr, nullptr, 0.0, 1, W, 1, true, st, ctr);
         if (rc != FB_OK) return rc;
     } else {
         // natural [z][y][x] -> A layout [z][x][y]
@@ -832,12 +891,12 @@ FB_EXPORT int fb_convolve_host(int dim, double *vg, double *wg, const int64_t *s
         if ((rc = launch_transpose(w0, w1, Dz, H, W, st)) != FB_OK) return rc;
         cur = Pair{v1, w1};
         spare = Pair{v0, w0};
-        rc = run_sweep(1, num_iter, ax[0], cur, spare, nullptr, nullptr, nullptr, 0.0, Dz, W, H, true, st);
+        rc = run_sweep(1, num_iter, ax[0], cur, spare, nullptr, nullptr, nullptr, 0.0, Dz, W, H, true, st, ctr);
         if (rc != FB_OK) return rc;
-        rc = run_sweep(0, num_iter, ax[1], cur, spare, nullptr, nullptr, nullptr, 0.0, Dz, H, W, true, st);
+        rc = run_sweep(0, num_iter, ax[1], cur, spare, nullptr, nullptr, nullptr, 0.0, Dz, H, W, true, st, ctr);
         if (rc != FB_OK) return rc;
         if (dim == 3) {
-            rc = run_sweep(0, num_iter, ax[2], cur, spare, nullptr, nullptr, nullptr, 0.0, 1, Dz, H * W, true, st);
+            rc = run_sweep(0, num_iter, ax[2], cur, spare, nullptr, nullptr, nullptr, 0.0, 1, Dz, H * W, true, st, ctr);
             if (rc != FB_OK) return rc;
         }
     }
@@ -941,7 +1000,7 @@ int slab_carve(SlabLayout &s, char *base, const fb_problem *pr, const Derived &d
     const size_t R = (size_t)nsamples << pr->dim;
     memset(&s.inj, 0, sizeof s.inj);
     s.inj.mm = (unsigned long long *)take(FB_MM_STRIDE * 8);
-    s.inj.counters = (unsigned long long *)take(4 * 8);
+    s.inj.counters = (unsigned long long *)take((4 + kSweepCounterSlots) * 8);
     s.inj.offsets = (long long *)take(2 * 8);
     s.inj.first_mask = (unsigned char *)take((size_t)nsamples + 1);
     s.inj.rec_k = (int *)take(R * 4 + 4);
@@ -1015,9 +1074,10 @@ FB_EXPORT int fb_slab_phase1_dev(const fb_problem *prob, int64_t z_begin, int64_
     if ((rc = run_inject(prob, d, nsamples, nullptr, d_pts, d_val, w, st, z_begin, z_count)) != FB_OK) return rc;
     // x sweep (A -> B, transposing) and y sweep (in place) on the own planes
     Pair cur{w.vA, w.wA}, spare{w.vB, w.wB};
-    rc = run_sweep(1, prob->num_iter, d.ax[0], cur, spare, nullptr, nullptr, w.mm, d.csf, z_count, d.W, d.H, true, st);
+    SweepCounters ctr{w.counters + 4, 0};
+    rc = run_sweep(1, prob->num_iter, d.ax[0], cur, spare, nullptr, nullptr, w.mm, d.csf, z_count, d.W, d.H, true, st, ctr);
     if (rc != FB_OK) return rc;
-    rc = run_sweep(0, prob->num_iter, d.ax[1], cur, spare, nullptr, nullptr, w.mm, d.csf, z_count, d.H, d.W, true, st);
+    rc = run_sweep(0, prob->num_iter, d.ax[1], cur, spare, nullptr, nullptr, w.mm, d.csf, z_count, d.H, d.W, true, st, ctr);
     if (rc != FB_OK) return rc;
     if (cur.v != w.vB) {   // per-pass ping-pong may end in the other pair: bring the result home
         CUDA_TRY(cudaMemcpyAsync(w.vB, cur.v, (size_t)plane * z_count * 8, cudaMemcpyDeviceToDevice, st));
@@ -1043,7 +1103,8 @@ FB_EXPORT int fb_slab_phase2_dev(const fb_problem *prob, int64_t z_begin, int64_
     const long long plane = d.W * d.H;
     // fused z sweep + mask + divide + cast over the extended lines (A is free again: spare)
     Pair cur{s.vB, s.wB}, spare{s.vA, s.wA};
-    rc = run_sweep(2, prob->num_iter, d.ax[2], cur, spare, s.out_ext, s.out64_ext, s.inj.mm, d.csf, 1, z_ext, plane, true, st);
+    SweepCounters ctr{s.inj.counters + 4, 6};
+    rc = run_sweep(2, prob->num_iter, d.ax[2], cur, spare, s.out_ext, s.out64_ext, s.inj.mm, d.csf, 1, z_ext, plane, true, st, ctr);
     if (rc != FB_OK) return rc;
     CUDA_TRY(cudaMemcpyAsync(d_out, s.out_ext + halo_lo * plane, (size_t)plane * z_count * 4, cudaMemcpyDeviceToDevice, st));
     if (d_out64)
