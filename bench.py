@@ -64,7 +64,8 @@ def config_dict(fields_per_gpu, n_gpus):
             'fields_per_gpu_per_step': fields_per_gpu, 'fields_per_step': fields_per_gpu * n_gpus,
             'grid': list(SIZE), 'samples_per_field': N_PER_FIELD, 'parallelism': 'fields sharded, no collective',
             'cache': 'working set per step (%.1f GB fp64 state) exceeds L2; no flush needed'
-                     % (fields_per_gpu * POINTS_PER_FIELD * 32 / 1e9)}
+                     % (fields_per_gpu * POINTS_PER_FIELD * 32 / 1e9),
+            'streams': 'device-resident arm: consecutive batches alternate over 2 CUDA streams (own workspace each)'}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -204,8 +205,25 @@ def run_gpu(args, rank, local_rank, world):
     pin_val = torch.from_numpy(val_h.reshape(F * N_PER_FIELD)).pin_memory()
     d_pts = pin_pts.to(dev, non_blocking=True)
     d_val = pin_val.to(dev, non_blocking=True)
-    plan = fbi.BarnesDevice(2, SIGMA, X0, STEP, SIZE, nfields=F, nsamples=F * N_PER_FIELD, num_iter=NUM_ITER, device=dev)
+    # one plan (workspace + output buffer) per stream: consecutive batches alternate between the
+    # streams so that the zero-fill / injection of batch i+1 overlaps the sweeps of batch i
+    nstreams = max(1, args.streams)
+    plans = [fbi.BarnesDevice(2, SIGMA, X0, STEP, SIZE, nfields=F, nsamples=F * N_PER_FIELD, num_iter=NUM_ITER, device=dev)
+             for _ in range(nstreams)]
+    streams = [torch.cuda.Stream(device=dev) for _ in range(nstreams)]
+    plan = plans[0]
     torch.cuda.synchronize()
+
+    def run_steps(n):
+        """ n batches, round-robin over the streams; returns after enqueueing (caller synchronises) """
+        cur = torch.cuda.current_stream()
+        for s_ in streams:
+            s_.wait_stream(cur)
+        for i in range(n):
+            with torch.cuda.stream(streams[i % nstreams]):
+                plans[i % nstreams](d_pts, d_val)
+        for s_ in streams:
+            cur.wait_stream(s_)
 
     def barrier():
         torch.cuda.synchronize()
@@ -213,8 +231,7 @@ def run_gpu(args, rank, local_rank, world):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        plan(d_pts, d_val)
+    run_steps(args.warmup)
     barrier()
 
     sampler = ClockSampler(local_rank)
@@ -229,8 +246,7 @@ def run_gpu(args, rank, local_rank, world):
     barrier()
     t_begin = time.perf_counter()
     ev0.record()
-    for _ in range(args.steps):
-        plan(d_pts, d_val)
+    run_steps(args.steps)
     ev1.record()
     barrier()
     t_end = time.perf_counter()
@@ -340,6 +356,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--fields', type=int, default=64, help='fields per GPU per step')
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--streams', type=int, default=2, help='device-resident arm: batches alternate over this many streams')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
@@ -353,7 +370,7 @@ def main():
         cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', str(args.gpus),
                '--master-addr', '127.0.0.1', '--master-port', str(29500 + os.getpid() % 1000), os.path.abspath(__file__),
                '--gpus', str(args.gpus), '--steps', str(args.steps), '--warmup', str(args.warmup),
-               '--fields', str(args.fields)]
+               '--fields', str(args.fields), '--streams', str(args.streams)]
         sys.exit(subprocess.call(cmd))
     run_gpu(args, rank, local_rank, world)
 
