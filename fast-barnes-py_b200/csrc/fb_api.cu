@@ -24,6 +24,7 @@ namespace {
 thread_local std::string g_err;
 std::atomic<long long> g_launches{0};
 std::atomic<int> g_profiling{0};
+std::atomic<int> g_three_warp{1};   // tuning switch: three-stage sweep kernels on/off
 std::atomic<int> g_two_warp{1};     // tuning switch (fb_set_option): two-warp sweep kernels on/off
 
 int fail(int code, const char *fmt, ...)
@@ -97,6 +98,7 @@ struct AxisParams { int T; double alpha; };
 
 // ---- sweeps ------------------------------------------------------------------------------------
 constexpr size_t kSmemLimit = 227 * 1024 - 1024;   // opt-in dynamic smem per CTA, minus slack
+constexpr size_t kSmemPerSM = 228 * 1024;          // shared memory of one SM (each CTA also reserves 1 KB)
 
 int sm_count(int dev)
 {
@@ -135,7 +137,16 @@ size_t sweep_smem_bytes(int npass, int mode, int D)
 
 // two-warp kernel: split of npass into (NA, NB); B gets the smaller half except that the
 // finalising sweep (MODE 2, expensive division in warp B) gives B a single pass when npass >= 3
-inline int sweep2_na(int npass, int mode) { return mode == 2 ? npass : (npass + 1) / 2; }
+std::atomic<int> g_na_shift{0};     // tuning: moves passes between the two warps of fb_sweep2_kernel
+inline int sweep2_na(int npass, int mode)
+{
+    if (mode == 2) return npass;
+    // warp A also does the global loads and prefetches: it gets the smaller share (measured)
+    int na = (npass - 1) / 2 + g_na_shift.load();
+    if (na < 1) na = 1;
+    if (na > npass - 1) na = npass - 1;
+    return na;
+}
 
 size_t sweep2_smem_bytes(int npass, int mode, int D)
 {
@@ -196,13 +207,99 @@ int launch_sweep2_m(int npass, const FbSweep &p, size_t smem, cudaStream_t st)
     } else {
         switch (npass * 10 + na) {
         case 21: return launch_sweep2_t<1, 1, MODE>(p, smem, st);
+        case 31: return launch_sweep2_t<1, 2, MODE>(p, smem, st);
         case 32: return launch_sweep2_t<2, 1, MODE>(p, smem, st);
+        case 41: return launch_sweep2_t<1, 3, MODE>(p, smem, st);
         case 42: return launch_sweep2_t<2, 2, MODE>(p, smem, st);
+        case 52: return launch_sweep2_t<2, 3, MODE>(p, smem, st);
         case 53: return launch_sweep2_t<3, 2, MODE>(p, smem, st);
+        case 62: return launch_sweep2_t<2, 4, MODE>(p, smem, st);
         case 63: return launch_sweep2_t<3, 3, MODE>(p, smem, st);
         }
     }
     return fail(FB_EINVAL, "unsupported pass split: %d/%d", npass, na);
+}
+
+// three-warp kernel: stage split (S0, S1, S2) of npass passes
+inline void sweep3_split(int npass, int mode, int &s0, int &s1, int &s2)
+{
+    if (mode == 2) {            // last stage only finalises (divisions)
+        s2 = 0;
+        s1 = npass / 2;
+        s0 = npass - s1;
+    } else {                    // first stage also loads: give it the smaller share
+        s0 = npass / 3;
+        if (s0 < 1) s0 = 1;
+        s2 = (npass - s0) / 2;
+        s1 = npass - s0 - s2;
+    }
+}
+
+size_t sweep3_smem_bytes(int npass, int mode, int D)
+{
+    const int U = FB_SWEEP_U;
+    const int R = sweep_ring_depth(D);
+    int s0, s1, s2;
+    sweep3_split(npass, mode, s0, s1, s2);
+    const int H0 = (D + 2 * U + U - 1) / U * U;
+    const int H1 = s2 > 0 ? H0 : 2 * U;
+    const int nrings = (s0 - 1) + (s1 - 1) + (s2 > 0 ? s2 - 1 : 0);
+    size_t b = ((size_t)nrings * R + H0 + H1) * 32 * sizeof(double);
+    if (mode == 1) b += (size_t)FB_TILE3_K * FB_TILE3_PITCH * sizeof(double);
+    return b;
+}
+
+template <int S0, int S1, int S2, int MODE>
+int launch_sweep3_t(const FbSweep &p, size_t smem, cudaStream_t st)
+{
+    static thread_local size_t configured[16] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (smem > 48 * 1024 && configured[dev & 15] < smem) {
+        CUDA_TRY(cudaFuncSetAttribute(fb_sweep3_kernel<S0, S1, S2, MODE, FB_SWEEP_U>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)kSmemLimit));
+        CUDA_TRY(cudaFuncSetAttribute(fb_sweep3_kernel<S0, S1, S2, MODE, FB_SWEEP_U>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                      cudaSharedmemCarveoutMaxShared));
+        configured[dev & 15] = kSmemLimit;
+    }
+    const long long nitems = p.n_outer * p.n_groups;
+    if (nitems <= 0) return FB_OK;
+    static thread_local int occ[16] = {0};
+    static thread_local size_t occ_smem[16] = {0};
+    if (occ[dev & 15] == 0 || occ_smem[dev & 15] != smem) {
+        int nb = 0;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fb_sweep3_kernel<S0, S1, S2, MODE, FB_SWEEP_U>, 96, smem));
+        occ[dev & 15] = nb > 0 ? nb : 1;
+        occ_smem[dev & 15] = smem;
+    }
+    long long grid = (long long)occ[dev & 15] * sm_count(dev);
+    if (grid > nitems) grid = nitems;
+    CUDA_TRY(cudaMemsetAsync(p.work_counter, 0, sizeof(unsigned long long), st));
+    fb_sweep3_kernel<S0, S1, S2, MODE, FB_SWEEP_U><<<(unsigned)grid, 96, smem, st>>>(p);
+    LAUNCH_CHECK();
+    return FB_OK;
+}
+
+template <int MODE>
+int launch_sweep3_m(int npass, const FbSweep &p, size_t smem, cudaStream_t st)
+{
+    if constexpr (MODE == 2) {
+        switch (npass) {
+        case 2: return launch_sweep3_t<1, 1, 0, MODE>(p, smem, st);
+        case 3: return launch_sweep3_t<2, 1, 0, MODE>(p, smem, st);
+        case 4: return launch_sweep3_t<2, 2, 0, MODE>(p, smem, st);
+        case 5: return launch_sweep3_t<3, 2, 0, MODE>(p, smem, st);
+        case 6: return launch_sweep3_t<3, 3, 0, MODE>(p, smem, st);
+        }
+    } else {
+        switch (npass) {
+        case 3: return launch_sweep3_t<1, 1, 1, MODE>(p, smem, st);
+        case 4: return launch_sweep3_t<1, 2, 1, MODE>(p, smem, st);
+        case 5: return launch_sweep3_t<1, 2, 2, MODE>(p, smem, st);
+        case 6: return launch_sweep3_t<2, 2, 2, MODE>(p, smem, st);
+        }
+    }
+    return fail(FB_EINVAL, "unsupported three-stage split of %d passes", npass);
 }
 
 template <int NPASS, int MODE, int U>
@@ -316,7 +413,19 @@ int run_sweep(int mode, int num_iter, AxisParams ax, Pair &cur, Pair &spare, flo
         // two warps per 16 lines when the launch fuses >= 2 passes (general chunk length only)
         const bool two_warps = g_two_warp.load() && (np >= 2 || m == 2) && sweep_chunk(p.D) == FB_SWEEP_U &&
                                sweep2_smem_bytes(np, m, p.D) <= kSmemLimit;
-        if (two_warps) {
+        // three stages when the launch has enough passes and the extra hand-over ring still lets
+        // the same number of CTAs fit on an SM
+        const bool three_warps = two_warps && (m == 2 ? g_three_warp.load() != 0 : g_three_warp.load() > 1) &&
+                                 (m == 2 ? np >= 2 : np >= 3) &&
+                                 sweep3_smem_bytes(np, m, p.D) <= kSmemLimit &&
+                                 (kSmemPerSM / (sweep3_smem_bytes(np, m, p.D) + 1024)) >=
+                                     (kSmemPerSM / (sweep2_smem_bytes(np, m, p.D) + 1024));
+        if (three_warps) {
+            const size_t smem = sweep3_smem_bytes(np, m, p.D);
+            if (m == 0) rc = launch_sweep3_m<0>(np, p, smem, st);
+            else if (m == 1) rc = launch_sweep3_m<1>(np, p, smem, st);
+            else rc = launch_sweep3_m<2>(np, p, smem, st);
+        } else if (two_warps) {
             const size_t smem = sweep2_smem_bytes(np, m, p.D);
             if (m == 0) rc = launch_sweep2_m<0>(np, p, smem, st);
             else if (m == 1) rc = launch_sweep2_m<1>(np, p, smem, st);
@@ -1294,6 +1403,8 @@ FB_EXPORT int fb_set_option(const char *name, int value)
 {
     if (!name) return fail(FB_EINVAL, "null option name");
     if (!strcmp(name, "two_warp_sweeps")) { g_two_warp.store(value ? 1 : 0); return FB_OK; }
+    if (!strcmp(name, "three_warp_sweeps")) { g_three_warp.store(value ? 1 : 0); return FB_OK; }
+    if (!strcmp(name, "sweep2_na_shift")) { g_na_shift.store(value); return FB_OK; }
     if (!strcmp(name, "host_chunk_fields")) { g_host_chunk_fields.store(value); return FB_OK; }
     return fail(FB_EINVAL, "unknown option: %s", name);
 }
