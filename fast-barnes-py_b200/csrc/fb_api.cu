@@ -483,6 +483,25 @@ int derive(const fb_problem *pr, Derived &d)
     return FB_OK;
 }
 
+// ---- 1D segmentation plan --------------------------------------------------------------------------
+struct SegPlan { bool on; long long seg_len, halo, n_seg, Le; };
+
+SegPlan seg_plan(const fb_problem *pr, const Derived &d)
+{
+    SegPlan s{false, 0, 0, 0, 0};
+    if (pr->dim != 1 || pr->nfields != 1 || !(pr->flags & FB_FLAG_SEGMENTED_1D)) return s;
+    s.halo = (long long)pr->num_iter * (d.ax[0].T + 1);
+    long long seg = (d.W + 18943) / 18944;                 // about two rounds of 16-segment work items on 148 SMs
+    if (seg < 4 * s.halo) seg = 4 * s.halo;                 // halo overhead <= 50 %
+    if (seg < 256) seg = 256;
+    seg = (seg + 63) / 64 * 64;
+    s.seg_len = seg;
+    s.n_seg = (d.W + seg - 1) / seg;
+    s.Le = seg + 2 * s.halo;
+    s.on = s.n_seg >= 2 && d.W >= s.Le;
+    return s;
+}
+
 // ---- workspace -----------------------------------------------------------------------------------
 struct Workspace {
     double *vA, *wA, *vB, *wB;
@@ -493,11 +512,12 @@ struct Workspace {
     double *rec_w, *rec_wv;
     long long *seg_node;
     unsigned int *seg_base, *seg_n;
+    double *seg[4];          // 1D segmented path: extended segments (v, w) x (in, out)
     size_t bytes;
 };
 
 // carve (base may be nullptr to only compute the size)
-void carve(Workspace &w, char *base, const fb_problem *pr, long long total, long long nsamples)
+void carve(Workspace &w, char *base, const fb_problem *pr, long long total, long long nsamples, const SegPlan *sp = nullptr)
 {
     size_t off = 0;
     auto take = [&](size_t n) { char *p = base ? base + off : nullptr; off += align_up(n); return p; };
@@ -517,6 +537,8 @@ void carve(Workspace &w, char *base, const fb_problem *pr, long long total, long
     w.seg_node = (long long *)take(R * 8 + 8);
     w.seg_base = (unsigned int *)take(R * 4 + 4);
     w.seg_n = (unsigned int *)take(R * 4 + 4);
+    for (int i = 0; i < 4; ++i)
+        w.seg[i] = (sp && sp->on) ? (double *)take((size_t)sp->Le * sp->n_seg * sizeof(double)) : nullptr;
     w.bytes = off;
 }
 
@@ -599,13 +621,29 @@ int run_inject(const fb_problem *pr, const Derived &d, long long nsamples, const
     return FB_OK;
 }
 
-int run_sweeps(const fb_problem *pr, const Derived &d, Workspace &w, float *d_out, double *d_out64, cudaStream_t st)
+int run_sweeps(const fb_problem *pr, const Derived &d, Workspace &w, float *d_out, double *d_out64, cudaStream_t st,
+               const SegPlan &sp)
 {
     const long long nf = pr->nfields;
     const int n = pr->num_iter;
     Pair cur{w.vA, w.wA}, spare{w.vB, w.wB};
     SweepCounters ctr{w.counters + 4, 0};
     int rc;
+    if (pr->dim == 1 && sp.on) {
+        // segmented 1D: gather the extended segments side by side, sweep them as independent lines
+        // (transposing output -> one contiguous run per segment), finalise
+        dim3 gg((unsigned)((sp.Le + 31) / 32), (unsigned)((sp.n_seg + 31) / 32), 2);
+        if (gg.y > 65535) return fail(FB_EINVAL, "too many segments");
+        fb_seg_gather_kernel<<<gg, 256, 0, st>>>(w.vA, w.wA, w.seg[0], w.seg[1], d.W, sp.seg_len, sp.halo, sp.n_seg, sp.Le);
+        LAUNCH_CHECK();
+        Pair scur{w.seg[0], w.seg[1]}, sspare{w.seg[2], w.seg[3]};
+        rc = run_sweep(1, n, d.ax[0], scur, sspare, nullptr, nullptr, w.mm, d.csf, 1, sp.Le, sp.n_seg, true, st, ctr);
+        if (rc != FB_OK) return rc;
+        fb_seg_finalize_kernel<<<(unsigned)((d.W + 255) / 256), 256, 0, st>>>(scur.v, scur.w, d_out, d_out64, d.W, sp.seg_len,
+                                                                             sp.halo, sp.Le, w.mm, d.csf);
+        LAUNCH_CHECK();
+        return prof_mark(3, st);
+    }
     if (pr->dim == 1) {
         rc = run_sweep(2, n, d.ax[0], cur, spare, d_out, d_out64, w.mm, d.csf, nf, d.W, 1, true, st, ctr);
         if (rc != FB_OK) return rc;
@@ -650,7 +688,8 @@ int pipeline(const fb_problem *pr, long long nsamples, const int64_t *h_offsets,
         if (rc != FB_OK) return rc;
     }
     Workspace w;
-    carve(w, (char *)d_ws, pr, d.total, nsamples);
+    const SegPlan sp = seg_plan(pr, d);
+    carve(w, (char *)d_ws, pr, d.total, nsamples, &sp);
     if ((long long)w.bytes > ws_bytes) return fail(FB_ENOMEM, "workspace too small: need %zu bytes, got %lld", w.bytes, ws_bytes);
     g_prof.launches_begin = g_launches.load();
     g_prof.marked = 0;
@@ -658,7 +697,7 @@ int pipeline(const fb_problem *pr, long long nsamples, const int64_t *h_offsets,
     rc = run_inject(pr, d, nsamples, h_offsets, d_pts, d_val, w, st);
     if (rc != FB_OK) return rc;
     if ((rc = prof_mark(2, st)) != FB_OK) return rc;
-    rc = run_sweeps(pr, d, w, d_out, d_out64, st);
+    rc = run_sweeps(pr, d, w, d_out, d_out64, st, sp);
     if (rc != FB_OK) return rc;
     g_prof.launches_end = g_launches.load();
     g_prof.armed = g_profiling.load() != 0;
@@ -787,7 +826,8 @@ FB_EXPORT int64_t fb_workspace_bytes(const fb_problem *prob, int64_t nsamples)
     Derived d;
     if (derive(prob, d) != FB_OK) return FB_EINVAL;
     Workspace w;
-    carve(w, nullptr, prob, d.total, nsamples);
+    const SegPlan sp = seg_plan(prob, d);
+    carve(w, nullptr, prob, d.total, nsamples, &sp);
     return (int64_t)w.bytes;
 }
 
@@ -859,7 +899,8 @@ FB_EXPORT int fb_barnes_host(const fb_problem *prob, int64_t nsamples, const int
         if (n > max_chunk_samples) max_chunk_samples = n;
     }
     Workspace w;
-    carve(w, nullptr, &cp, d.total, max_chunk_samples);
+    const SegPlan sp = seg_plan(&cp, d);
+    carve(w, nullptr, &cp, d.total, max_chunk_samples, &sp);
     const size_t ws_slot = align_up(w.bytes);
     const size_t cgrid = (size_t)cf * d.total;
     const size_t stg_slot = align_up((size_t)max_chunk_samples * prob->dim * 8) + align_up((size_t)max_chunk_samples * 8) +

@@ -71,12 +71,17 @@ def _check_samples(pts, val):
     return pts
 
 
-def _problem(dim, sigma, x0, step, size, method_id, num_iter, max_dist_weight, nfields=1):
+FLAG_SEGMENTED_1D = 1
+# 1D grids longer than this are swept in overlapping segments unless exact=True is requested
+SEGMENTED_1D_THRESHOLD = 1 << 16
+
+
+def _problem(dim, sigma, x0, step, size, method_id, num_iter, max_dist_weight, nfields=1, flags=0):
     p = _lib.FbProblem()
     p.dim = dim
     p.method = method_id
     p.num_iter = int(num_iter)
-    p.flags = 0
+    p.flags = int(flags)
     p.nfields = int(nfields)
     for m in range(3):
         p.size[m] = int(size[m]) if m < dim else 1
@@ -102,7 +107,7 @@ def _check_kernel_vs_grid(method, sigma, step, size, num_iter):
 # ---------------------------------------------------------------------------------------------
 
 def barnes(pts, val, sigma, x0, step, size, method='optimized_convolution',
-           num_iter=4, max_dist=3.5, min_weight=0.001, *, return_float64=False):
+           num_iter=4, max_dist=3.5, min_weight=0.001, *, return_float64=False, exact=None):
     """
     Barnes interpolation of the observation values `val` at the sample points `pts` with
     Gaussian width `sigma` on the regular grid (`x0`, `step`, `size`) in 1, 2 or 3 dimensions.
@@ -116,6 +121,11 @@ def barnes(pts, val, sigma, x0, step, size, method='optimized_convolution',
 
     return_float64=True returns `(field32, field64)` where field64 is the fp64 quotient
     `vg/wg + offset` before the float32 cast (interpolation.py:367).
+
+    exact (1D only): a 1D grid is a single line whose accumulator chain cannot be parallelised
+    bit-exactly.  exact=True walks it sequentially (bit-identical to the reference, slow for long
+    grids); exact=False cuts it into overlapping segments swept in parallel (rounding-level
+    differences).  Default None: exact up to 65536 grid points, segmented above.
     """
     pts = _check_samples(pts, val)
     dim = pts.shape[1]
@@ -127,8 +137,11 @@ def barnes(pts, val, sigma, x0, step, size, method='optimized_convolution',
 
     if method in _CONV_METHODS:
         _check_kernel_vs_grid(method, sigma, step, size, num_iter)
+        flags = 0
+        if dim == 1 and (exact is False or (exact is None and size[0] > SEGMENTED_1D_THRESHOLD)):
+            flags |= FLAG_SEGMENTED_1D
         return _run(pts, val, sigma, x0, step, size, _CONV_METHODS[method], num_iter, max_dist_weight,
-                    return_float64=return_float64)
+                    return_float64=return_float64, flags=flags)
     if method in ('radius', 'naive'):
         raise NotImplementedError("method '" + method + "' is outside the scope of the B200 path "
                                   "(use 'optimized_convolution' or 'convolution')")
@@ -136,14 +149,14 @@ def barnes(pts, val, sigma, x0, step, size, method='optimized_convolution',
 
 
 def _run(pts, val, sigma, x0, step, size, method_id, num_iter, max_dist_weight, offsets=None, nfields=1,
-         return_float64=False):
+         return_float64=False, flags=0):
     dim = len(size)
     if pts.shape[0] == 0:
         # np.amin of an empty array (reference: _normalize_values, :209)
         raise ValueError('zero-size array to reduction operation minimum which has no identity')
     pts_c = np.ascontiguousarray(pts, dtype=np.float64)
     val_c = np.ascontiguousarray(val, dtype=np.float64)
-    prob = _problem(dim, sigma, x0, step, size, method_id, num_iter, max_dist_weight, nfields)
+    prob = _problem(dim, sigma, x0, step, size, method_id, num_iter, max_dist_weight, nfields, flags)
     shape = tuple(size[::-1]) if nfields == 1 and offsets is None else (nfields,) + tuple(size[::-1])
     out = np.empty(shape, dtype=np.float32)
     out64 = np.empty(shape, dtype=np.float64) if return_float64 else None

@@ -40,6 +40,11 @@ extern "C" {
 #define FB_ENOMEM   -3   /* workspace too small / allocation failed */
 #define FB_EKERNEL  -4   /* rectangular kernel does not fit (grid or on-chip ring storage) */
 
+/* fb_problem.flags */
+#define FB_FLAG_SEGMENTED_1D 1   /* dim 1, nfields 1: cut the single grid line into overlapping segments that are
+                                    swept in parallel (exact in exact arithmetic, rounding-level difference to the
+                                    reference's single accumulator chain); default is the bit-exact sequential walk */
+
 #define FB_METHOD_OPTIMIZED_CONVOLUTION 0   /* interpolation.py:169-176 */
 #define FB_METHOD_CONVOLUTION           1   /* interpolation.py:178-185 */
 
@@ -49,7 +54,7 @@ typedef struct fb_problem {
     int32_t dim;             /* 1, 2 or 3 */
     int32_t method;          /* FB_METHOD_* */
     int32_t num_iter;        /* number of self-convolutions n */
-    int32_t flags;           /* reserved, 0 */
+    int32_t flags;           /* FB_FLAG_* */
     int64_t nfields;         /* independent fields on the same grid (>= 1) */
     int64_t size[3];         /* grid extension (x, y, z) */
     double  sigma[3];        /* Gaussian width per axis */

@@ -421,6 +421,41 @@ def test_properties_full_size(fb):
     assert np.allclose(b[~np.isnan(b)], 2.0 * a[~np.isnan(a)], rtol=3e-7, atol=0)
 
 
+def test_1d_segmented_vs_exact(fb, orc):
+    """ 1D: the default for long grids cuts the single line into overlapping segments.  Exact in
+    exact arithmetic; vs the reference the fp64 quotient differs by the reference's own accumulated
+    rounding (its accumulator runs over the whole line; grows ~sqrt(L)).  Tolerance: 1e-8 * value
+    range on the fp64 quotient for L = 2^18, NaN mask identical, float32 identical on > 99.9 % of
+    the points and within 8 ulp everywhere.  exact=True stays bit-identical. """
+    rng = np.random.default_rng(1234)
+    L = 2 ** 18
+    N = L // 64
+    pts = rng.uniform(0, L - 1, N)
+    val = rng.normal(0, 1, N)
+    vrange = val.max() - val.min()
+    for n, sigma in ((4, 32.0), (6, 32.0), (5, 3.0), (1, 10.0)):
+        ref = orc._interpolate_opt_convol(pts.reshape(-1, 1), val.copy(), np.asarray([sigma]), np.zeros(1), np.ones(1),
+                                          (L,), n, exp(-3.5 ** 2 / 2), stages=True)
+        a32, a64 = fb.barnes(pts, val, sigma, 0.0, 1.0, L, num_iter=n, return_float64=True)      # default: segmented
+        assert np.array_equal(np.isnan(a64), np.isnan(ref['out64']))
+        m = ~np.isnan(ref['out64'])
+        assert np.max(np.abs(a64[m] - ref['out64'][m])) <= 1e-8 * vrange, (n, sigma)
+        assert np.mean(a32[m] != ref['out32'][m]) < 1e-3
+        ulp = np.abs(a32[m].view(np.int32).astype(np.int64) - ref['out32'][m].view(np.int32).astype(np.int64))
+        assert ulp.max() <= 8
+        if n == 4:
+            e32, e64 = fb.barnes(pts, val, sigma, 0.0, 1.0, L, num_iter=n, return_float64=True, exact=True)
+            assert bits_equal(e64, ref['out64']) and bits_equal(e32, ref['out32'])
+    # short grids take the exact path by default
+    Ls = 5000
+    p2 = rng.uniform(0, Ls - 1, 200)
+    v2 = rng.normal(5, 2, 200)
+    assert bits_equal(fb.barnes(p2, v2, 12.0, 0.0, 1.0, Ls), orc.barnes(p2.reshape(-1, 1), v2, 12.0, 0.0, 1.0, (Ls,)))
+    seg = fb.barnes(p2, v2, 12.0, 0.0, 1.0, Ls, exact=False)               # forcing segments on a short grid works too
+    ex = fb.barnes(p2, v2, 12.0, 0.0, 1.0, Ls)
+    assert np.array_equal(np.isnan(seg), np.isnan(ex)) and np.nanmax(np.abs(seg - ex)) <= 1e-5
+
+
 def test_z_slab_decomposition_single_gpu(fb):
     """ 3D z-slabs, emulated on one GPU: own planes are injected and x/y-swept per slab,
     halo planes copied between slabs, fused z sweep per slab.  Tolerance: the x/y stages are
