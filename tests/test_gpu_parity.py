@@ -534,6 +534,34 @@ def test_barnes_s2_golden(fbS2, res):
     assert bits_equal(out2, out) and bits_equal(p1[0], lam)
 
 
+def test_s2_res64_vs_oracle(fbS2, orc):
+    """ BASELINE configs[3]: 4800x2400 lon/lat grid, Lambert grid 4096x2816, T=54 (wide rings) """
+    g = load_golden('c1_paper')
+    step = 1.0 / 64
+    x0 = np.asarray([-26.0 + step, 34.5])
+    size = (4800, 2400)
+    out = fbS2.barnes_S2(g['pts'], g['val'], 1.0, x0, step, size, method='optimized_convolution_S2', num_iter=4)
+    ref = orc.barnes_S2(g['pts'], g['val'], 1.0, x0, step, size, num_iter=4, nthreads=8)
+    assert out.shape == ref.shape == (2400, 4800)
+    assert np.array_equal(np.isnan(out), np.isnan(ref))
+    m = ~np.isnan(ref)
+    assert np.max(np.abs(out[m] - ref[m]) / np.abs(ref[m])) <= S2_RTOL
+    assert np.mean(out[m] != ref[m]) < 0.01
+
+
+def test_nan_and_constant_values(fb):
+    """ np.amin/np.amax propagate NaN: one NaN observation makes the whole field NaN (reference
+    behaviour of _normalize_values); identical observations give offset == value and 0/w + value """
+    rng = np.random.default_rng(4)
+    pts = rng.uniform(1, 5, (50, 2))
+    val = rng.normal(0, 1, 50)
+    val[7] = np.nan
+    res = fb.barnes(pts, val, 0.5, [0.0, 0.0], 0.1, (64, 64))
+    assert np.all(np.isnan(res))
+    res = fb.barnes(pts, np.full(50, -3.25), 0.5, [0.0, 0.0], 0.1, (64, 64))
+    assert np.all(res[~np.isnan(res)] == np.float32(-3.25)) and (~np.isnan(res)).sum() > 500
+
+
 def test_resample_exact_on_reference_field(fbS2):
     """ resampling alone, fed with the reference's own Lambert field: the only non-libm inputs are
     the per-row rho and per-column sin/cos tables """
