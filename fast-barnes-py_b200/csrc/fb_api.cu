@@ -850,7 +850,7 @@ namespace {
 constexpr int kHostStreams = 3;
 cudaStream_t g_host_streams[kHostStreams] = {nullptr, nullptr, nullptr};
 int g_host_streams_device = -1;
-std::atomic<int> g_host_chunk_fields{16};
+std::atomic<int> g_host_chunk_fields{4};
 
 int host_streams_get()
 {

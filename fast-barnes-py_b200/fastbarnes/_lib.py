@@ -14,7 +14,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.normpath(os.path.join(_HERE, '..', 'csrc'))
-LIB_PATH = os.path.join(CSRC, '_build', 'libfastbarnes_b200.so')
+LIB_PATH = os.environ.get('FB_LIB_PATH') or os.path.join(CSRC, '_build', 'libfastbarnes_b200.so')
 
 FB_OK, FB_EINVAL, FB_ECUDA, FB_ENOMEM, FB_EKERNEL = 0, -1, -2, -3, -4
 METHOD_OPTIMIZED_CONVOLUTION, METHOD_CONVOLUTION = 0, 1

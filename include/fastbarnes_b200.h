@@ -165,7 +165,7 @@ int fb_barnes_s2_host(int64_t nsamples, const double *pts, const double *val, co
  *   "two_warp_sweeps" (default 1): sweep launches that fuse >= 2 passes use two warps per 16 lines
  *   "three_warp_sweeps" (default 1): 0 off, 1 three pipeline stages for the finalising sweep, 2 for all
  *   "sweep2_na_shift" (default 0): moves passes between the two warps of the two-warp kernel
- *   "host_chunk_fields" (default 16): fields per chunk of the pipelined fb_barnes_host path      */
+ *   "host_chunk_fields" (default 4): fields per chunk of the pipelined fb_barnes_host path      */
 int  fb_set_option(const char *name, int value);
 
 /* ---- introspection for benchmarks --------------------------------------------------------- */

@@ -266,12 +266,12 @@ def test_chunked_host_pipeline_and_kernel_variants(fb):
         p3 = pts[:offs[1]][None].repeat(6, axis=0) + rng.uniform(0, 0.01, (6, counts[0], 1))
         v3 = rng.normal(0, 1, (6, counts[0]))
         b = fb.barnes_batched(p3, v3, 1.2, [0.0, 0.0], 0.1, size, num_iter=5)
-        _lib.check(L.fb_set_option(b'host_chunk_fields', 16))
+        _lib.check(L.fb_set_option(b'host_chunk_fields', 4))
         b_ref = fb.barnes_batched(p3, v3, 1.2, [0.0, 0.0], 0.1, size, num_iter=5)
         _lib.check(L.fb_set_option(b'two_warp_sweeps', 0))
         c = fb.barnes_batched(pts, val, 1.2, [0.0, 0.0], 0.1, size, sample_offsets=offs, num_iter=4)
     finally:
-        L.fb_set_option(b'host_chunk_fields', 16)
+        L.fb_set_option(b'host_chunk_fields', 4)
         L.fb_set_option(b'two_warp_sweeps', 1)
     assert bits_equal(a, ref) and bits_equal(c, ref) and bits_equal(b, b_ref)
     for i in range(len(counts)):
