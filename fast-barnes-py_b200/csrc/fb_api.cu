@@ -12,6 +12,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -25,7 +26,9 @@ thread_local std::string g_err;
 std::atomic<long long> g_launches{0};
 std::atomic<int> g_profiling{0};
 thread_local bool t_skip_counter_zero = false;   // co-run: the work counter is shared and already zeroed
-std::atomic<int> g_tmem{0};         // experimental: 1 = tensor-memory sweep kernel instead of the shared-memory ones
+// tensor-memory use of the sweeps: 0 none, 1 the all-TMEM one-warp kernel, 2 that kernel next to the
+// shared-memory kernels, 3 (default) the hybrid kernel for launches with enough work items
+std::atomic<int> g_tmem{3};
 std::atomic<int> g_three_warp{1};   // tuning switch: three-stage sweep kernels on/off
 std::atomic<int> g_two_warp{1};     // tuning switch (fb_set_option): two-warp sweep kernels on/off
 
@@ -111,6 +114,13 @@ int sm_count(int dev)
         cached[dev & 15] = n;
     }
     return cached[dev & 15];
+}
+
+int sm_count_current()
+{
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return sm_count(dev);
 }
 
 // Work counters of the persistent sweep launches: one slot per launch of a call, zeroed on the
@@ -304,6 +314,84 @@ int launch_sweep3_m(int npass, const FbSweep &p, size_t smem, cudaStream_t st)
     return fail(FB_EINVAL, "unsupported three-stage split of %d passes", npass);
 }
 
+// hybrid kernel: two two-warp pipelines per CTA, private rings in tensor memory
+inline void sweeph_split(int npass, int &na, int &nb) { na = npass / 2; nb = npass - na; }
+inline int sweeph_tmem_cols(int npass, int D)
+{
+    int na, nb;
+    sweeph_split(npass, na, nb);
+    const int rings = (nb - 1) > (na - 1) ? (nb - 1) : (na - 1);
+    int need = rings * sweep_ring_depth(D) * 2, cols = 32;
+    while (cols < need) cols *= 2;
+    return cols;
+}
+size_t sweeph_smem_bytes(int mode, int D)
+{
+    const int U = FB_SWEEP_U;
+    const int R2 = (D + 2 * U + U - 1) / U * U;
+    size_t b = (size_t)R2 * 32 * sizeof(double);
+    if (mode == 1) b += (size_t)FB_TILE_K * FB_TILE_PITCH * sizeof(double);
+    return 2 * b;
+}
+inline bool sweeph_fits(int npass, int D)
+{
+    return npass >= 2 && npass <= 6 && sweep_chunk(D) == FB_SWEEP_U && sweeph_tmem_cols(npass, D) <= 128 &&
+           2 * (sweeph_smem_bytes(1, D) + 1024) <= kSmemPerSM;      // at least two CTAs (four pipelines) per SM
+}
+
+template <int NA, int NB, int MODE>
+int launch_sweeph_t(FbSweep p, int npass, cudaStream_t st)
+{
+    static thread_local size_t configured[16] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const size_t smem = sweeph_smem_bytes(MODE, p.D);
+    if (smem > 40 * 1024 && configured[dev & 15] < smem) {     // static shared memory counts too
+        CUDA_TRY(cudaFuncSetAttribute(fb_sweeph_kernel<NA, NB, MODE, FB_SWEEP_U>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)kSmemLimit));
+        CUDA_TRY(cudaFuncSetAttribute(fb_sweeph_kernel<NA, NB, MODE, FB_SWEEP_U>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                      cudaSharedmemCarveoutMaxShared));
+        configured[dev & 15] = kSmemLimit;
+    }
+    const long long nitems = p.n_outer * p.n_groups;
+    if (nitems <= 0) return FB_OK;
+    p.tmem_cols = sweeph_tmem_cols(npass, p.D);
+    // CTAs per SM: 128 registers x 128 threads (launch bounds) -> 4 by registers; shared memory and
+    // tensor-memory columns bound it further (the occupancy API reports 0 for this kernel)
+    int occ_est = 4;
+    if ((int)(kSmemPerSM / (smem + 1024)) < occ_est) occ_est = (int)(kSmemPerSM / (smem + 1024));
+    if (occ_est < 1) occ_est = 1;
+    int per_sm = occ_est;
+    if (per_sm * p.tmem_cols > 512) per_sm = 512 / p.tmem_cols;      // tensor-memory columns bound the CTAs per SM
+    long long grid = (long long)per_sm * sm_count(dev);
+    if (grid > (nitems + 1) / 2) grid = (nitems + 1) / 2;
+    if (getenv("FB_DEBUG")) fprintf(stderr, "[fb] sweeph<%d,%d,%d> smem %zu occ %d tmem_cols %d per_sm %d grid %lld items %lld\n", NA, NB, MODE, smem, occ_est, p.tmem_cols, per_sm, grid, nitems);
+    CUDA_TRY(cudaMemsetAsync(p.work_counter, 0, sizeof(unsigned long long), st));
+    fb_sweeph_kernel<NA, NB, MODE, FB_SWEEP_U><<<(unsigned)grid, 128, smem, st>>>(p);
+    LAUNCH_CHECK();
+    return FB_OK;
+}
+
+template <int MODE>
+int launch_sweeph_m(int npass, const FbSweep &p, cudaStream_t st)
+{
+    switch (npass) {
+    case 2: return launch_sweeph_t<1, 1, MODE>(p, npass, st);
+    case 3: return launch_sweeph_t<1, 2, MODE>(p, npass, st);
+    case 4: return launch_sweeph_t<2, 2, MODE>(p, npass, st);
+    case 5: return launch_sweeph_t<2, 3, MODE>(p, npass, st);
+    case 6: return launch_sweeph_t<3, 3, MODE>(p, npass, st);
+    }
+    return fail(FB_EINVAL, "unsupported number of fused passes: %d", npass);
+}
+
+int launch_sweeph(int m, int npass, const FbSweep &p, cudaStream_t st)
+{
+    if (m == 0) return launch_sweeph_m<0>(npass, p, st);
+    if (m == 1) return launch_sweeph_m<1>(npass, p, st);
+    return launch_sweeph_m<2>(npass, p, st);
+}
+
 // tensor-memory kernel: 4 warps per CTA, one CTA per SM (it allocates all 512 TMEM columns)
 inline bool sweep_tmem_fits(int npass, int D)
 {
@@ -466,6 +554,13 @@ int run_sweep(int mode, int num_iter, AxisParams ax, Pair &cur, Pair &spare, flo
             p.out_w = spare.w;
         }
         int rc = FB_OK;
+        if (g_tmem.load() == 3 && sweeph_fits(np, p.D) && p.n_outer * p.n_groups >= 8LL * sm_count_current()) {
+            // hybrid: two-warp pipelines, private rings in tensor memory, 8 pipelines per SM
+            rc = launch_sweeph(m, np, p, st);
+            if (rc != FB_OK) return rc;
+            if (m != 2 && !in_place) { Pair t2 = cur; cur = spare; spare = t2; }
+            continue;
+        }
         if (g_tmem.load() == 1 && sweep_tmem_fits(np, p.D)) {
             // experimental: rings in tensor memory, this kernel alone
             rc = launch_sweep_tmem(m, np, p, st, true);
