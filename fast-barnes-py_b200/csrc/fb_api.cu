@@ -7,6 +7,7 @@
 // entry point that computes fails with FB_ECUDA when no device is present.
 #include "../../include/fastbarnes_b200.h"
 #include "fb_kernels.cuh"
+#include "fb_exact.cuh"
 
 #include <atomic>
 #include <cmath>
@@ -1293,6 +1294,114 @@ FB_EXPORT int fb_inject_host(const fb_problem *prob, int64_t nsamples, const int
             offsets[b] = m[2] ? NAN : (dec(m[0]) + dec(m[1])) / 2.0;
         }
     }
+    return FB_OK;
+}
+
+// ---- exact Gaussian sums: methods 'naive', 'radius', 'naive_S2' ("next" row N3) ---------------------------
+namespace {
+template <int KIND, int DIM>
+int launch_exact_t(const FbExact &p, cudaStream_t st)
+{
+    const long long total = p.W * p.H * p.Dz;
+    const long long blocks = (total + FB_EXACT_THREADS - 1) / FB_EXACT_THREADS;
+    if (blocks > 2147483647LL) return fail(FB_EINVAL, "grid too large for the exact-sum kernel");
+    fb_exact_kernel<KIND, DIM><<<(unsigned)blocks, FB_EXACT_THREADS, 0, st>>>(p);
+    LAUNCH_CHECK();
+    return FB_OK;
+}
+
+int run_exact(const fb_problem *pr, long long n, const double *d_pts, const double *d_val, double min_weight,
+              double *d_out, unsigned long long *scratch, cudaStream_t st)
+{
+    if (!pr) return fail(FB_EINVAL, "null problem");
+    const int dim = pr->dim, method = pr->method;
+    if (method != FB_METHOD_NAIVE && method != FB_METHOD_RADIUS && method != FB_METHOD_NAIVE_S2)
+        return fail(FB_EINVAL, "not an exact-sum method: %d", method);
+    if (dim < 1 || dim > 3) return fail(FB_EINVAL, "Barnes interpolation supports only sample points in dimensions 1, 2 or 3");
+    if (pr->nfields != 1) return fail(FB_EINVAL, "the exact-sum methods take one field per call");
+    if (n < 1) return fail(FB_EINVAL, "no samples");
+    if (method == FB_METHOD_RADIUS) {
+        // interpolation.py:187-193
+        if (dim != 2) return fail(FB_EINVAL, "radius algorithm works only in 2D but data is: %dD", dim);
+        if (pr->sigma[0] != pr->sigma[1]) return fail(FB_EINVAL, "radius algorithm in 2D works only for scalar sigma value");
+        if (!(min_weight > 0.0)) return fail(FB_EINVAL, "min_weight must be positive");
+    }
+    if (method == FB_METHOD_NAIVE_S2 && dim != 2) return fail(FB_EINVAL, "naive_S2 needs (lon, lat) sample points");
+    FbExact p{};
+    p.pts = d_pts;
+    p.val = d_val;
+    p.n = n;
+    p.mm = scratch;
+    p.W = pr->size[0];
+    p.H = dim > 1 ? pr->size[1] : 1;
+    p.Dz = dim > 2 ? pr->size[2] : 1;
+    if (p.W < 1 || p.H < 1 || p.Dz < 1) return fail(FB_EINVAL, "grid size must be positive");
+    for (int m = 0; m < 3; ++m) {
+        p.x0[m] = m < dim ? pr->x0[m] : 0.0;
+        p.step[m] = m < dim ? pr->step[m] : 1.0;
+        p.scale[m] = m < dim ? 2 * (pr->sigma[m] * pr->sigma[m]) : 1.0;     // scale = 2*sigma**2  (:872)
+    }
+    if (method == FB_METHOD_RADIUS) {
+        const double search_radius = std::sqrt(-2.0 * std::log(min_weight)) * pr->sigma[0];    // :823
+        p.radius_sqr = search_radius * search_radius;                                          // kdtree.py:249
+        p.max_dist_weight = pr->max_dist_weight;
+    }
+    p.out = d_out;
+    fb_init_kernel<<<1, 32, 0, st>>>(scratch, 1, scratch + FB_MM_STRIDE);
+    LAUNCH_CHECK();
+    FbSamples sm{};
+    sm.pts = d_pts;
+    sm.val = d_val;
+    sm.offsets = nullptr;
+    sm.n_uniform = n;
+    long long mmb = (n + 256 * 8 - 1) / (256 * 8);
+    if (mmb > 1024) mmb = 1024;
+    fb_minmax_kernel<<<dim3((unsigned)mmb, 1), 256, 0, st>>>(sm, scratch);
+    LAUNCH_CHECK();
+    if (method == FB_METHOD_NAIVE_S2) return launch_exact_t<1, 2>(p, st);
+    if (method == FB_METHOD_RADIUS) return launch_exact_t<2, 2>(p, st);
+    if (dim == 1) return launch_exact_t<0, 1>(p, st);
+    if (dim == 2) return launch_exact_t<0, 2>(p, st);
+    return launch_exact_t<0, 3>(p, st);
+}
+}  // namespace
+
+FB_EXPORT int fb_barnes_exact_dev(const fb_problem *prob, int64_t nsamples, const double *d_pts, const double *d_val,
+                                  double min_weight, double *d_out64, void *d_scratch, void *stream)
+{
+    int rc = require_device();
+    if (rc != FB_OK) return rc;
+    if (!d_pts || !d_val || !d_out64 || !d_scratch) return fail(FB_EINVAL, "null device pointer");
+    return run_exact(prob, nsamples, d_pts, d_val, min_weight, d_out64, (unsigned long long *)d_scratch,
+                     (cudaStream_t)stream);
+}
+
+FB_EXPORT int fb_barnes_exact_host(const fb_problem *prob, int64_t nsamples, const double *pts, const double *val,
+                                   double min_weight, double *out64)
+{
+    int rc = require_device();
+    if (rc != FB_OK) return rc;
+    if (!prob || !pts || !val || !out64) return fail(FB_EINVAL, "null pointer");
+    if (prob->dim < 1 || prob->dim > 3 || nsamples < 1) return fail(FB_EINVAL, "invalid argument");
+    size_t total = 1;
+    for (int m = 0; m < prob->dim; ++m) {
+        if (prob->size[m] < 1) return fail(FB_EINVAL, "grid size must be positive");
+        total *= (size_t)prob->size[m];
+    }
+    const size_t npts = (size_t)nsamples * prob->dim;
+    std::lock_guard<std::mutex> lock(g_arena_mutex);
+    void *stg = nullptr;
+    if ((rc = arena_get(1, align_up(npts * 8) + align_up((size_t)nsamples * 8) + align_up(total * 8) + 2048, &stg)) != FB_OK)
+        return rc;
+    Staging s((char *)stg);
+    double *d_pts = s.take<double>(npts), *d_val = s.take<double>((size_t)nsamples), *d_out = s.take<double>(total);
+    unsigned long long *scratch = s.take<unsigned long long>(32);
+    cudaStream_t st = 0;
+    CUDA_TRY(cudaMemcpyAsync(d_pts, pts, npts * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_val, val, (size_t)nsamples * 8, cudaMemcpyHostToDevice, st));
+    if ((rc = run_exact(prob, nsamples, d_pts, d_val, min_weight, d_out, scratch, st)) != FB_OK) return rc;
+    CUDA_TRY(cudaMemcpyAsync(out64, d_out, total * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
     return FB_OK;
 }
 

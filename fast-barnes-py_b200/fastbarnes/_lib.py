@@ -18,6 +18,7 @@ LIB_PATH = os.environ.get('FB_LIB_PATH') or os.path.join(CSRC, '_build', 'libfas
 
 FB_OK, FB_EINVAL, FB_ECUDA, FB_ENOMEM, FB_EKERNEL = 0, -1, -2, -3, -4
 METHOD_OPTIMIZED_CONVOLUTION, METHOD_CONVOLUTION = 0, 1
+METHOD_NAIVE, METHOD_RADIUS, METHOD_NAIVE_S2 = 2, 3, 4
 
 c_double_p = ctypes.POINTER(ctypes.c_double)
 c_float_p = ctypes.POINTER(ctypes.c_float)
@@ -65,6 +66,10 @@ SIGNATURES = {
                                         c_double_p, ctypes.c_double]),
     'fb_inject_host': (ctypes.c_int, [ctypes.POINTER(FbProblem), ctypes.c_int64, c_i64_p, c_double_p,
                                       c_double_p, c_double_p, c_double_p, c_double_p]),
+    'fb_barnes_exact_host': (ctypes.c_int, [ctypes.POINTER(FbProblem), ctypes.c_int64, c_double_p, c_double_p,
+                                            ctypes.c_double, c_double_p]),
+    'fb_barnes_exact_dev': (ctypes.c_int, [ctypes.POINTER(FbProblem), ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p,
+                                           ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     'fb_lambert_create_proj': (ctypes.c_int, [ctypes.c_double] * 4 + [c_double_p]),
     'fb_lambert_to_map_host': (ctypes.c_int, [c_double_p, c_double_p, ctypes.c_int64, c_double_p]),
     'fb_s2_part1_host': (ctypes.c_int, [ctypes.c_int64, c_double_p, c_double_p, c_double_p, c_double_p,

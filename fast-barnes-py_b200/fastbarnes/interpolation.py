@@ -116,8 +116,10 @@ def barnes(pts, val, sigma, x0, step, size, method='optimized_convolution',
     (index order [y, x] / [z, y, x]), NaN where the nearest sample is farther than
     `max_dist * sigma`; the caller's arrays are never modified.
 
-    Supported methods: 'optimized_convolution' (default) and 'convolution'.  The O(N*W*H)
-    methods 'naive' and 'radius' are outside this package's scope and raise RuntimeError.
+    Methods: 'optimized_convolution' (default) and 'convolution' (float32 result), and the
+    exact O(N*W*H) Gaussian sums 'naive' and 'radius' (float64 result like the reference; every
+    grid point sums the samples in sample order, 'radius' by exhaustive search instead of the
+    reference's kd-tree, so they agree with the reference to rounding, not bit for bit).
 
     return_float64=True returns `(field32, field64)` where field64 is the fp64 quotient
     `vg/wg + offset` before the float32 cast (interpolation.py:367).
@@ -142,10 +144,31 @@ def barnes(pts, val, sigma, x0, step, size, method='optimized_convolution',
             flags |= FLAG_SEGMENTED_1D
         return _run(pts, val, sigma, x0, step, size, _CONV_METHODS[method], num_iter, max_dist_weight,
                     return_float64=return_float64, flags=flags)
-    if method in ('radius', 'naive'):
-        raise NotImplementedError("method '" + method + "' is outside the scope of the B200 path "
-                                  "(use 'optimized_convolution' or 'convolution')")
+    if method == 'radius':
+        # specific checks of the reference (interpolation.py:187-193)
+        if dim != 2:
+            raise RuntimeError('radius algorithm works only in 2D but data is: ' + str(dim) + 'D')
+        if sigma[0] != sigma[1]:
+            raise RuntimeError('radius algorithm in 2D works only for scalar sigma value but sigma is: ' + str(sigma))
+        return _run_exact(pts, val, sigma, x0, step, size, _lib.METHOD_RADIUS, max_dist_weight, min_weight)
+    if method == 'naive':
+        return _run_exact(pts, val, sigma, x0, step, size, _lib.METHOD_NAIVE, max_dist_weight, min_weight)
     raise RuntimeError("encountered invalid Barnes interpolation method: " + method)
+
+
+def _run_exact(pts, val, sigma, x0, step, size, method_id, max_dist_weight, min_weight):
+    """ The exact Gaussian sums 'naive' / 'radius' / 'naive_S2' (reference interpolation.py:862-938,
+    :809-855, interpolationS2.py:260-301): float64 field of shape size[::-1]. """
+    if pts.shape[0] == 0:
+        raise ValueError('zero-size array to reduction operation minimum which has no identity')
+    pts_c = np.ascontiguousarray(pts, dtype=np.float64)
+    val_c = np.ascontiguousarray(val, dtype=np.float64)
+    prob = _problem(len(size), sigma, x0, step, size, method_id, 1, max_dist_weight, 1, 0)
+    out = np.empty(tuple(size[::-1]), dtype=np.float64)
+    rc = _lib.lib().fb_barnes_exact_host(prob, pts_c.shape[0], _lib.dptr(pts_c), _lib.dptr(val_c),
+                                         float(min_weight), _lib.dptr(out))
+    _lib.check(rc)
+    return out
 
 
 def _run(pts, val, sigma, x0, step, size, method_id, num_iter, max_dist_weight, offsets=None, nfields=1,

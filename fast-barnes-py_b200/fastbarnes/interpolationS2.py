@@ -1,18 +1,19 @@
 # -*- coding: utf-8 -*-
 """
 B200-native drop-in for `fastbarnes.interpolationS2` of MeteoSwiss/fast-barnes-py (v2.0.0),
-restricted to method 'optimized_convolution_S2': the samples are projected to a fixed Lambert
-conformal map, the Euclidean optimized convolution runs on the fixed Lambert grid
-(lam_x0 = (-32, -2), 64 x 44 degrees), and the Lambert field is bilinearly resampled to the
-requested lon/lat grid (reference interpolationS2.py:144-254).  All three steps are CUDA
-kernels behind include/fastbarnes_b200.h; there is no CPU fallback.
+method 'optimized_convolution_S2': the samples are projected to a fixed Lambert conformal map,
+the Euclidean optimized convolution runs on the fixed Lambert grid (lam_x0 = (-32, -2),
+64 x 44 degrees), and the Lambert field is bilinearly resampled to the requested lon/lat grid
+(reference interpolationS2.py:144-254); method 'naive_S2' is the exact Gaussian sum over
+spherical distances (:260-301).  All steps are CUDA kernels behind include/fastbarnes_b200.h;
+there is no CPU fallback.
 """
 from math import exp
 
 import numpy as np
 
 from . import _lib
-from .interpolation import _per_axis, _grid_size
+from .interpolation import _per_axis, _grid_size, _run_exact
 from .util import lambert_conformal
 
 __all__ = ['barnes_S2', 'interpolate_opt_convol_S2_part1', 'interpolate_opt_convol_S2_part2', 'get_lambert_proj']
@@ -26,9 +27,10 @@ def barnes_S2(pts, val, sigma, x0, step, size, method='optimized_convolution', n
     (interpolationS2.py:32-138): float32 array of shape (size[1], size[0]), or the Lambert-grid
     field of shape (int(44/step), int(64/step)) if `resample` is False.
 
-    Accepted methods: 'optimized_convolution_S2'.  The reference's default string
-    'optimized_convolution' is not accepted by the reference itself (it raises RuntimeError);
-    here it is taken as an alias of 'optimized_convolution_S2'.  'naive_S2' is out of scope.
+    Accepted methods: 'optimized_convolution_S2' and 'naive_S2' (the exact Gaussian sum over
+    spherical distances, float64 result; agrees with the reference to rounding).  The reference's
+    default string 'optimized_convolution' is not accepted by the reference itself (it raises
+    RuntimeError); here it is taken as an alias of 'optimized_convolution_S2'.
     """
     dim = pts.shape[1]
     sigma = _per_axis('sigma', sigma, dim)
@@ -40,7 +42,8 @@ def barnes_S2(pts, val, sigma, x0, step, size, method='optimized_convolution', n
     if method in ('optimized_convolution_S2', 'optimized_convolution'):
         return _interpolate_opt_convol_S2(pts, val, sigma, x0, step, size, num_iter, max_dist_weight, resample)
     if method == 'naive_S2':
-        raise NotImplementedError("method 'naive_S2' is outside the scope of the B200 path")
+        pts_c, val_c = _samples(pts, val)
+        return _run_exact(pts_c, val_c, sigma, x0, step, size, _lib.METHOD_NAIVE_S2, max_dist_weight, 0.0)
     raise RuntimeError("encountered invalid Barnes interpolation method: " + str(method))
 
 

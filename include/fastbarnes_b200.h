@@ -47,6 +47,10 @@ extern "C" {
 
 #define FB_METHOD_OPTIMIZED_CONVOLUTION 0   /* interpolation.py:169-176 */
 #define FB_METHOD_CONVOLUTION           1   /* interpolation.py:178-185 */
+/* exact Gaussian sums (fb_barnes_exact_*), the reference's accuracy yardsticks */
+#define FB_METHOD_NAIVE                 2   /* interpolation.py:195-196, :862-938 */
+#define FB_METHOD_RADIUS                3   /* interpolation.py:187-193, :809-855 */
+#define FB_METHOD_NAIVE_S2              4   /* interpolationS2.py:134-135, :260-301 */
 
 /* Problem description shared by the interpolation entry points
  * (the arguments of _interpolate_opt_convol, interpolation.py:329). */
@@ -136,6 +140,21 @@ int fb_convolve_host(int dim, double *vg, double *wg, const int64_t *size,
  * them; vg, wg [nfields][z][y][x] HOST grids receive the injected fields.                   */
 int fb_inject_host(const fb_problem *prob, int64_t nsamples, const int64_t *sample_offsets,
                    const double *pts, const double *val, double *vg, double *wg, double *offsets);
+
+/* ---- exact Gaussian sums ("next" row N3) --------------------------------------------------- */
+/* prob->method = FB_METHOD_NAIVE (_interpolate_naive, interpolation.py:862-938; dim 1-3),
+ * FB_METHOD_RADIUS (_interpolate_radius, :809-855; dim 2, sigma[0] == sigma[1]; the kd-tree search
+ * of util/kdtree.py is an exhaustive scan with the same inclusion rule; uses prob->max_dist_weight
+ * and min_weight) or FB_METHOD_NAIVE_S2 (_interpolate_naive_S2, interpolationS2.py:260-301; pts
+ * are (lon, lat) in degrees).  nfields must be 1; num_iter and flags are ignored.
+ * out64 [z][y][x] float64 like the reference (no float32 cast).  Every grid point sums the
+ * samples in sample order; the reference sums with np.dot / np.sum or in kd-tree order, so
+ * results agree to rounding (~1e-13 relative), not bit for bit.                               */
+int fb_barnes_exact_host(const fb_problem *prob, int64_t nsamples, const double *pts, const double *val,
+                         double min_weight, double *out64);
+/* same on DEVICE buffers; d_scratch: >= 256 bytes of device memory; enqueues on `stream`. */
+int fb_barnes_exact_dev(const fb_problem *prob, int64_t nsamples, const double *d_pts, const double *d_val,
+                        double min_weight, double *d_out64, void *d_scratch, void *stream);
 
 /* ---- S2 path ------------------------------------------------------------------------------ */
 /* util/lambert_conformal.py:50-94 create_proj -> proj[5] = (center_lon, n, n_inv, F, rho0) */

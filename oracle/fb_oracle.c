@@ -441,6 +441,71 @@ FBO_API void fbo_resample(const float *lam_field, int64_t lam_w, const double *l
     }
 }
 
+/* ------------------------------------------------------------------------- */
+/* Exact Gaussian sums ("next" row N3: the accuracy yardsticks).
+ *   kind 0: fastbarnes/interpolation.py:862-938  _interpolate_naive (1D/2D/3D)
+ *   kind 1: fastbarnes/interpolationS2.py:260-301 _interpolate_naive_S2 with _dist_S2
+ *   kind 2: fastbarnes/interpolation.py:809-855  _interpolate_radius (2D); the kd-tree radius
+ *           search (util/kdtree.py:297-329, inclusion rule `sqr_dist <= radius**2`) is replaced by
+ *           an exhaustive scan with the same rule.
+ * The reference sums with np.dot / np.sum (kinds 0, 1) or in kd-tree traversal order (kind 2);
+ * this restatement sums in sample order, so it matches the reference to rounding (~1e-13
+ * relative), not bit for bit -- the tests state the tolerance.
+ * val is centred in place; out [z][y][x] float64; returns the offset.                          */
+FBO_API double fbo_interpolate_exact(int kind, int dim, const double *pts, double *val, int64_t n,
+                                     const double *sigma, const double *x0, const double *step,
+                                     const int64_t *size, double max_dist_weight, double min_weight,
+                                     double *out, int nthreads)
+{
+    const double offset = fbo_normalize_values(val, n);
+    const int64_t W = size[0], H = dim > 1 ? size[1] : 1, Dz = dim > 2 ? size[2] : 1;
+    double scale[3] = {1.0, 1.0, 1.0};
+    for (int m = 0; m < dim; m++) scale[m] = 2 * (sigma[m] * sigma[m]);
+    const double rad_per_degree = M_PI / 180.0;
+    const double search_radius = kind == 2 ? sqrt(-2.0 * log(min_weight)) * sigma[0] : 0.0;
+    const double radius_sqr = search_radius * search_radius;
+    (void)nthreads;
+#pragma omp parallel for collapse(2) schedule(static) num_threads(nthreads > 0 ? nthreads : 1)
+    for (int64_t k = 0; k < Dz; k++) {
+        for (int64_t j = 0; j < H; j++) {
+            const double zc = dim > 2 ? x0[2] + k * step[2] : 0.0;
+            const double yc = dim > 1 ? x0[1] + j * step[1] : 0.0;
+            for (int64_t i = 0; i < W; i++) {
+                const double xc = x0[0] + i * step[0];
+                double weighted_sum = 0.0, weight_total = 0.0;
+                for (int64_t s = 0; s < n; s++) {
+                    double weight;
+                    if (kind == 1) {
+                        const double lon1 = pts[2 * s], lat1 = pts[2 * s + 1];
+                        const double lat0_rad = yc * rad_per_degree, lat1_rad = lat1 * rad_per_degree;
+                        double arg = sin(lat0_rad) * sin(lat1_rad) +
+                                     cos(lat0_rad) * cos(lat1_rad) * cos((lon1 - xc) * rad_per_degree);
+                        if (arg > 1.0) arg = 1.0;
+                        const double dist = acos(arg) / rad_per_degree;
+                        weight = exp(-dist * dist / scale[0]);
+                    } else if (kind == 2) {
+                        const double dx = xc - pts[2 * s], dy = yc - pts[2 * s + 1];
+                        const double sqr_dist = dx * dx + dy * dy;
+                        if (!(sqr_dist <= radius_sqr)) continue;
+                        weight = exp(-sqr_dist / scale[0]);
+                    } else {
+                        const double dx = pts[dim * s] - xc;
+                        double sqr_dist = dx * dx / scale[0];
+                        if (dim > 1) { const double dy = pts[dim * s + 1] - yc; sqr_dist = sqr_dist + dy * dy / scale[1]; }
+                        if (dim > 2) { const double dz = pts[dim * s + 2] - zc; sqr_dist = sqr_dist + dz * dz / scale[2]; }
+                        weight = exp(-sqr_dist);
+                    }
+                    weighted_sum += weight * val[s];
+                    weight_total += weight;
+                }
+                const int keep = kind == 2 ? (weight_total >= max_dist_weight) : (weight_total > 0.0);
+                out[(k * H + j) * W + i] = keep ? weighted_sum / weight_total + offset : NAN;
+            }
+        }
+    }
+    return offset;
+}
+
 FBO_API int fbo_max_threads(void)
 {
 #ifdef _OPENMP

@@ -12,6 +12,9 @@ Fixtures (all inputs seeded, outputs produced by the reference's own functions):
   c1_paper.npz      the paper case (2400x1200, N=3490): inputs, sha256 of the float32
                     output, a strided sub-sample of the fp64 quotient and float32 output
   s2_*.npz          barnes_S2 at step 1/8 (full arrays) and 1/32 (digest + sub-sample)
+  exact_methods.npz 'naive', 'radius' and 'naive_S2' (the exact Gaussian sums) on small seeded
+                    cases and on the paper's samples at a coarse grid
+                    (only this one:  python oracle/gen_golden.py exact)
 """
 import hashlib
 import os
@@ -186,5 +189,51 @@ def main():
         print('s2 res', res, out.shape, lam.shape, np.isnan(out).mean())
 
 
+def exact_cases():
+    """ 'naive' / 'radius' (interpolation.py:862-938, :809-855) and 'naive_S2'
+    (interpolationS2.py:260-301) through the reference's public API. """
+    rng = np.random.default_rng(4242)
+    d = {}
+
+    def put(name, fn, pts, val, sigma, x0, step, size, **kw):
+        out = fn(pts, val, sigma, np.asarray(x0, dtype=np.float64) if not np.isscalar(x0) else x0, step, size, **kw)
+        assert out.dtype == np.float64
+        d[name + '_pts'], d[name + '_val'], d[name + '_out'] = pts, val, out
+        d[name + '_args'] = np.asarray(np.concatenate([np.atleast_1d(sigma).astype(float).ravel(),
+                                                       np.atleast_1d(x0).astype(float).ravel(),
+                                                       np.atleast_1d(step).astype(float).ravel(),
+                                                       np.atleast_1d(size).astype(float).ravel()]))
+        print(name, out.shape, np.isnan(out).mean())
+
+    p2 = rng.uniform(0, 10, (200, 2)); v2 = rng.normal(1000, 10, 200)
+    put('naive_2d', ref.barnes, p2, v2, [1.0, 1.0], [0.0, 0.0], [0.25, 0.25], (41, 37), method='naive')
+    put('naive_2d_aniso', ref.barnes, p2, v2, [1.0, 0.5], [0.0, 0.5], [0.25, 0.5], (41, 19), method='naive')
+    put('radius_2d', ref.barnes, p2, v2, [1.0, 1.0], [0.0, 0.0], [0.25, 0.25], (41, 37), method='radius')
+    ps = rng.uniform(0, 3, (20, 2)); vs = rng.normal(0, 1, 20)
+    put('radius_2d_sparse', ref.barnes, ps, vs, [0.5, 0.5], [0.0, 0.0], [0.25, 0.25], (41, 37), method='radius')
+    put('radius_2d_minw', ref.barnes, ps, vs, [0.5, 0.5], [0.0, 0.0], [0.25, 0.25], (41, 37), method='radius',
+        max_dist=2.0, min_weight=0.01)
+    p1 = rng.uniform(0, 10, (50, 1)); v1 = rng.normal(0, 1, 50)
+    put('naive_1d', ref.barnes, p1, v1, [0.7], [0.0], [0.1], (101,), method='naive')
+    p3 = rng.uniform(0, 5, (80, 3)); v3 = rng.normal(0, 1, 80)
+    put('naive_3d', ref.barnes, p3, v3, [1.0, 0.8, 0.6], [0.0, 0.0, 0.0], [0.5, 0.5, 0.5], (11, 9, 7), method='naive')
+    pl = np.column_stack([rng.uniform(-20, 30, 150), rng.uniform(35, 65, 150)]); vl = rng.normal(1000, 10, 150)
+    put('naive_S2', refS2.barnes_S2, pl, vl, [1.5, 1.5], [-20.0, 35.0], [1.0, 1.0], (51, 31), method='naive_S2')
+
+    sys.path.insert(0, os.path.join(REF, 'demo'))
+    import reader
+    pts, val = reader.read_csv_array(os.path.join(REF, 'demo', 'input', 'PressQFF_202007271200_3490.csv'))
+    put('paper_naive', ref.barnes, pts, val, [1.0, 1.0], [-26.0 + 0.5, 34.5], [0.5, 0.5], (150, 75), method='naive')
+    put('paper_radius', ref.barnes, pts, val, [1.0, 1.0], [-26.0 + 0.5, 34.5], [0.5, 0.5], (150, 75), method='radius')
+    put('paper_naive_S2', refS2.barnes_S2, pts, val, [1.0, 1.0], [-26.0 + 0.5, 34.5], [0.5, 0.5], (150, 75),
+        method='naive_S2')
+    del d['paper_radius_pts'], d['paper_radius_val'], d['paper_naive_S2_pts'], d['paper_naive_S2_val']
+    np.savez_compressed(os.path.join(OUT, 'exact_methods.npz'), **d)
+
+
 if __name__ == '__main__':
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == 'exact':
+        exact_cases()
+    else:
+        main()
+        exact_cases()

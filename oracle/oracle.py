@@ -78,6 +78,10 @@ def lib():
         L.fbo_resample.restype = None
         L.fbo_resample.argtypes = [_c_float_p, ctypes.c_int64, _c_double_p, _c_double_p, _c_double_p,
                                    _c_i64_p, _c_double_p, _c_float_p, ctypes.c_int]
+        L.fbo_interpolate_exact.restype = ctypes.c_double
+        L.fbo_interpolate_exact.argtypes = [ctypes.c_int, ctypes.c_int, _c_double_p, _c_double_p, ctypes.c_int64,
+                                            _c_double_p, _c_double_p, _c_double_p, _c_i64_p, ctypes.c_double,
+                                            ctypes.c_double, _c_double_p, ctypes.c_int]
         L.fbo_max_threads.restype = ctypes.c_int
         _lib = L
     return _lib
@@ -213,9 +217,22 @@ def _interpolate_opt_convol(pts, val, sigma, x0, step, size, num_iter, max_dist_
     return out32
 
 
+def _interpolate_exact(kind, pts, val, sigma, x0, step, size, max_dist_weight=0.0, min_weight=0.001, nthreads=1):
+    """ naive (kind 0, interpolation.py:862-938), naive_S2 (kind 1, interpolationS2.py:260-301) and
+    radius (kind 2, interpolation.py:809-855) summed in sample order; val is centred in place. """
+    dim = len(size)
+    pts = _f64(pts)
+    out = np.empty(tuple(size)[::-1], dtype=np.float64)
+    sz = np.asarray(size, dtype=np.int64)
+    lib().fbo_interpolate_exact(int(kind), dim, _dp(pts), _dp(val), len(val), _dp(_f64(sigma)), _dp(_f64(x0)),
+                                _dp(_f64(step)), sz.ctypes.data_as(_c_i64_p), float(max_dist_weight),
+                                float(min_weight), _dp(out), int(nthreads))
+    return out
+
+
 def barnes(pts, val, sigma, x0, step, size, method='optimized_convolution', num_iter=4, max_dist=3.5,
-           nthreads=1):
-    """ fastbarnes/interpolation.py:31-199, restricted to the two convolution methods. """
+           min_weight=0.001, nthreads=1):
+    """ fastbarnes/interpolation.py:31-199 (all four methods; 'radius' by exhaustive search). """
     pts = np.asarray(pts, dtype=np.float64)
     if pts.ndim == 1:
         pts = pts.reshape(-1, 1)
@@ -225,8 +242,19 @@ def barnes(pts, val, sigma, x0, step, size, method='optimized_convolution', num_
         size = (size,)
     size = tuple(int(s) for s in size)
     max_dist_weight = exp(-max_dist ** 2 / 2)
+    if method == 'naive':
+        return _interpolate_exact(0, pts, val, _vec(sigma, dim), _vec(x0, dim), _vec(step, dim), size,
+                                  nthreads=nthreads)
+    if method == 'radius':
+        sg = _vec(sigma, dim)
+        if dim != 2:
+            raise RuntimeError('radius algorithm works only in 2D but data is: ' + str(dim) + 'D')
+        if sg[0] != sg[1]:
+            raise RuntimeError('radius algorithm in 2D works only for scalar sigma value but sigma is: ' + str(sg))
+        return _interpolate_exact(2, pts, val, sg, _vec(x0, dim), _vec(step, dim), size, max_dist_weight,
+                                  min_weight, nthreads=nthreads)
     if method not in ('optimized_convolution', 'convolution'):
-        raise RuntimeError('oracle covers only the convolution methods: ' + str(method))
+        raise RuntimeError("encountered invalid Barnes interpolation method: " + str(method))
     return _interpolate_opt_convol(pts, val, _vec(sigma, dim), _vec(x0, dim), _vec(step, dim), size,
                                    num_iter, max_dist_weight, plain=(method == 'convolution'),
                                    nthreads=nthreads)
@@ -286,10 +314,13 @@ def interpolate_opt_convol_S2_part2(lam_field, lam_x0, x0, step, size, lambert_p
 
 def barnes_S2(pts, val, sigma, x0, step, size, method='optimized_convolution_S2', num_iter=4, max_dist=3.5,
               resample=True, nthreads=1):
-    """ fastbarnes/interpolationS2.py:32-138, 'optimized_convolution_S2' only. """
-    if method != 'optimized_convolution_S2':
-        raise RuntimeError('oracle covers only optimized_convolution_S2: ' + str(method))
+    """ fastbarnes/interpolationS2.py:32-138. """
     val = np.array(val, dtype=np.float64, copy=True)
+    if method == 'naive_S2':
+        return _interpolate_exact(1, np.asarray(pts, dtype=np.float64), val, _vec(sigma, 2), _vec(x0, 2),
+                                  _vec(step, 2), tuple(int(s) for s in size), nthreads=nthreads)
+    if method != 'optimized_convolution_S2':
+        raise RuntimeError("encountered invalid Barnes interpolation method: " + str(method))
     res1 = interpolate_opt_convol_S2_part1(pts, val, _vec(sigma, 2), _vec(x0, 2), _vec(step, 2),
                                            tuple(int(s) for s in size), num_iter,
                                            exp(-max_dist ** 2 / 2), nthreads=nthreads)

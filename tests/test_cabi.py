@@ -95,8 +95,11 @@ def test_argument_validation_like_reference():
         interpolation.barnes(pts, val, 1.0, [0, 0], 0.1, (50, 17))       # sigma/step = 10, n = 4: T = 8, kernel 17
     with pytest.raises(RuntimeError, match='invalid Barnes interpolation method'):
         interpolation.barnes(pts, val, 1.0, [0, 0], 0.1, (50, 50), method='nope')
-    with pytest.raises(RuntimeError):
-        interpolation.barnes(pts, val, 1.0, [0, 0], 0.1, (50, 50), method='naive')
+    # method-specific checks of 'radius' (reference interpolation.py:187-193)
+    with pytest.raises(RuntimeError, match='radius algorithm works only in 2D'):
+        interpolation.barnes(np.zeros((len(val), 3)), val, 1.0, [0, 0, 0], 0.1, (50, 50, 50), method='radius')
+    with pytest.raises(RuntimeError, match='works only for scalar sigma'):
+        interpolation.barnes(pts, val, [1.0, 2.0], [0, 0], 0.1, (50, 50), method='radius')
     with pytest.raises(RuntimeError, match='invalid Barnes interpolation method'):
         interpolationS2.barnes_S2(pts, val, 1.0, [0, 0], 0.1, (50, 50), method='nope')
 

@@ -571,3 +571,43 @@ def test_resample_exact_on_reference_field(fbS2):
     m = ~np.isnan(g['out'])
     assert np.array_equal(np.isnan(out), np.isnan(g['out']))
     assert np.max(np.abs(out[m] - g['out'][m]) / np.abs(g['out'][m])) <= S2_RTOL
+
+
+# ---------------------------------------------------------------------------------------------
+# exact Gaussian sums ("next" row N3): 'naive' / 'radius' / 'naive_S2'
+
+from test_oracle_golden import EXACT_CASES, exact_case, close_exact      # noqa: E402
+
+
+@pytest.mark.parametrize('name,method,s2', EXACT_CASES)
+def test_exact_methods_golden(fb, fbS2, orc, name, method, s2):
+    """ reference interpolation.py:862-938 (naive), :809-855 (radius), interpolationS2.py:260-301
+    (naive_S2) through the public API: against the reference's own output (fixture) and against
+    the oracle, to rounding (sums in sample order, CUDA libm vs glibc; tolerance in close_exact:
+    |a-b| <= 1e-11 + 1e-12 |b|, NaN masks identical). """
+    g = load_golden('exact_methods')
+    pts, val, sigma, x0, step, size, kw = exact_case(g, name)
+    val_before = val.copy()
+    out = (fbS2.barnes_S2 if s2 else fb.barnes)(pts, val, sigma, x0, step, size, method=method, **kw)
+    assert np.array_equal(val, val_before)
+    assert out.dtype == np.float64 and out.shape == size[::-1]
+    assert close_exact(out, g[name + '_out'])
+    ref = (orc.barnes_S2 if s2 else orc.barnes)(pts, val, sigma, x0, step, size, method=method, nthreads=4, **kw)
+    assert close_exact(out, ref)
+
+
+def test_exact_methods_agree_with_convolution(fb):
+    """ the yardstick use: the optimized convolution with n=4 approximates the exact sum; their RMSE on the
+    paper's samples at a coarse grid is small compared with the spread of the values, 'radius' equals
+    'naive' where the truncated weights are negligible, and a many-sample tile loop is covered """
+    g = load_golden('exact_methods')
+    pts, val = g['paper_naive_pts'], g['paper_naive_val']
+    x0, step, size = [-25.5, 34.5], 0.5, (150, 75)
+    naive = fb.barnes(pts, val, 1.0, x0, step, size, method='naive')
+    radius = fb.barnes(pts, val, 1.0, x0, step, size, method='radius')
+    conv = fb.barnes(pts, val, 1.0, x0, step, size, method='optimized_convolution', num_iter=6)
+    m = ~np.isnan(radius) & ~np.isnan(conv)
+    assert m.mean() > 0.8
+    assert np.median(np.abs(radius[m] - naive[m])) < 0.01         # min_weight = 0.001 truncation
+    rmse = np.sqrt(np.mean((conv[m] - naive[m]) ** 2))
+    assert rmse < 0.5 and rmse < 0.05 * np.std(val)

@@ -4,7 +4,8 @@ CPU tests (no GPU): the oracle (oracle/fb_oracle.c, a C restatement of the refer
   * the reference's own known-answer vectors (tests/AccumulationTest.py of the reference),
   * the committed golden fixtures produced by the unmodified reference (oracle/gen_golden.py),
   * the reference itself, imported live, when /root/reference exists (build container only).
-All comparisons are bit-exact.
+All comparisons are bit-exact, except the exact-sum methods (naive / radius / naive_S2), which are
+compared to rounding with the tolerance stated in close_exact().
 """
 import hashlib
 import os
@@ -136,6 +137,44 @@ def test_golden_s2():
     out = orc.barnes_S2(g['pts'], g['val'], 1.0, g['x0'], float(g['step']), size, num_iter=4, nthreads=2)
     lam = orc.barnes_S2(g['pts'], g['val'], 1.0, g['x0'], float(g['step']), size, num_iter=4, resample=False, nthreads=2)
     assert bits_equal(out, g['out']) and bits_equal(lam, g['lam'])
+
+
+EXACT_CASES = [  # name, method, S2
+    ('naive_2d', 'naive', False), ('naive_2d_aniso', 'naive', False), ('radius_2d', 'radius', False),
+    ('radius_2d_sparse', 'radius', False), ('radius_2d_minw', 'radius', False), ('naive_1d', 'naive', False),
+    ('naive_3d', 'naive', False), ('naive_S2', 'naive_S2', True), ('paper_naive', 'naive', False),
+    ('paper_radius', 'radius', False), ('paper_naive_S2', 'naive_S2', True)]
+
+
+def exact_case(g, name):
+    """ inputs of one exact_methods.npz case: (pts, val, sigma, x0, step, size, kwargs). """
+    src = name if name + '_pts' in g else 'paper_naive'
+    pts, val, args = g[src + '_pts'], g[src + '_val'], g[name + '_args']
+    dim = pts.shape[1]
+    sigma, x0, step = args[:dim], args[dim:2 * dim], args[2 * dim:3 * dim]
+    size = tuple(int(v) for v in args[3 * dim:4 * dim])
+    kw = dict(max_dist=2.0, min_weight=0.01) if name == 'radius_2d_minw' else {}
+    return pts, val, sigma, x0, step, size, kw
+
+
+def close_exact(a, b, atol=1e-11, rtol=1e-12):
+    """ The exact-sum methods are compared to rounding: the reference sums with np.dot / np.sum (BLAS /
+    pairwise order) or in kd-tree order, the restatements in sample order.  NaN masks must be identical. """
+    assert a.shape == b.shape and a.dtype == b.dtype == np.float64
+    nan = np.isnan(b)
+    assert np.array_equal(np.isnan(a), nan)
+    return np.all(np.abs(a[~nan] - b[~nan]) <= atol + rtol * np.abs(b[~nan]))
+
+
+@pytest.mark.parametrize('name,method,s2', EXACT_CASES)
+def test_golden_exact_methods(name, method, s2):
+    # 'naive' / 'radius' / 'naive_S2' of the reference (interpolation.py:862-938, :809-855,
+    # interpolationS2.py:260-301) vs the oracle's sample-order sums
+    g = load_golden('exact_methods')
+    pts, val, sigma, x0, step, size, kw = exact_case(g, name)
+    fn = orc.barnes_S2 if s2 else orc.barnes
+    out = fn(pts, val, sigma, x0, step, size, method=method, nthreads=4, **kw)
+    assert close_exact(out, g[name + '_out'])
 
 
 def test_thread_count_does_not_change_bits():
