@@ -1590,21 +1590,30 @@ int resample_dev(const float *d_lam, long long lamW, long long lamH, const doubl
     return FB_OK;
 }
 
-void s2_problem(fb_problem &p, const double *sigma, const double *step, int num_iter, double mdw)
+void s2_problem(fb_problem &p, const double *sigma, const double *step, int num_iter, double mdw, const fb_s2_map &map)
 {
     memset(&p, 0, sizeof p);
     p.dim = 2;
     p.method = FB_METHOD_OPTIMIZED_CONVOLUTION;
     p.num_iter = num_iter;
     p.nfields = 1;
-    // interpolationS2.py:187-188: the fixed grid in Lambert space
-    p.size[0] = (int64_t)(64.0 / step[0]);
-    p.size[1] = (int64_t)(44.0 / step[1]);
+    // interpolationS2.py:187-188: the grid in Lambert space, lam_size = int(extent / step)
+    p.size[0] = (int64_t)(map.lam_extent[0] / step[0]);
+    p.size[1] = (int64_t)(map.lam_extent[1] / step[1]);
     p.size[2] = 1;
-    p.x0[0] = -32.0;
-    p.x0[1] = -2.0;
+    p.x0[0] = map.lam_x0[0];
+    p.x0[1] = map.lam_x0[1];
     for (int m = 0; m < 2; ++m) { p.sigma[m] = sigma[m]; p.step[m] = step[m]; }
     p.max_dist_weight = mdw;
+}
+
+int check_map(const fb_s2_map *map)
+{
+    if (!map) return fail(FB_EINVAL, "null map");
+    if (!(map->lam_extent[0] > 0.0) || !(map->lam_extent[1] > 0.0)) return fail(FB_EINVAL, "map extent must be positive");
+    if (!(map->proj[1] != 0.0) || !std::isfinite(map->proj[3]) || !std::isfinite(map->proj[4]))
+        return fail(FB_EINVAL, "invalid Lambert projection constants");
+    return FB_OK;
 }
 
 // part1 on the device: d_lam receives the Lambert field; returns the staging layout it used
@@ -1640,15 +1649,28 @@ FB_EXPORT int fb_lambert_to_map_host(const double *geoc, double *mapc, int64_t n
     return FB_OK;
 }
 
-FB_EXPORT int fb_s2_part1_host(int64_t nsamples, const double *pts, const double *val, const double *sigma,
-                               const double *step, int num_iter, double max_dist_weight, const double *proj,
-                               float *lam_field)
+// interpolationS2.py:187-188, :208: the reference's fixed European map
+FB_EXPORT int fb_s2_default_map(fb_s2_map *map)
+{
+    if (!map) return fail(FB_EINVAL, "null pointer");
+    map->lam_x0[0] = -32.0;
+    map->lam_x0[1] = -2.0;
+    map->lam_extent[0] = 64.0;
+    map->lam_extent[1] = 44.0;
+    return fb_lambert_create_proj(11.5, 34.5, 42.5, 65.5, map->proj);
+}
+
+FB_EXPORT int fb_s2_part1_map_host(int64_t nsamples, const double *pts, const double *val, const double *sigma,
+                                   const double *step, int num_iter, double max_dist_weight, const fb_s2_map *map,
+                                   float *lam_field)
 {
     int rc = require_device();
     if (rc != FB_OK) return rc;
-    if (!pts || !val || !sigma || !step || !proj || !lam_field) return fail(FB_EINVAL, "null pointer");
+    if (!pts || !val || !sigma || !step || !lam_field) return fail(FB_EINVAL, "null pointer");
+    if ((rc = check_map(map)) != FB_OK) return rc;
+    const double *proj = map->proj;
     fb_problem lp;
-    s2_problem(lp, sigma, step, num_iter, max_dist_weight);
+    s2_problem(lp, sigma, step, num_iter, max_dist_weight, *map);
     Derived d;
     if ((rc = derive(&lp, d)) != FB_OK) return rc;
     std::lock_guard<std::mutex> lock(g_arena_mutex);
@@ -1669,6 +1691,18 @@ FB_EXPORT int fb_s2_part1_host(int64_t nsamples, const double *pts, const double
     CUDA_TRY(cudaMemcpyAsync(lam_field, d_lam, (size_t)d.total * 4, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     return FB_OK;
+}
+
+FB_EXPORT int fb_s2_part1_host(int64_t nsamples, const double *pts, const double *val, const double *sigma,
+                               const double *step, int num_iter, double max_dist_weight, const double *proj,
+                               float *lam_field)
+{
+    if (!proj) return fail(FB_EINVAL, "null pointer");
+    fb_s2_map map;
+    int rc = fb_s2_default_map(&map);
+    if (rc != FB_OK) return rc;
+    memcpy(map.proj, proj, sizeof map.proj);
+    return fb_s2_part1_map_host(nsamples, pts, val, sigma, step, num_iter, max_dist_weight, &map, lam_field);
 }
 
 FB_EXPORT int fb_s2_resample_host(const float *lam_field, int64_t lam_w, int64_t lam_h, const double *lam_x0,
@@ -1693,15 +1727,17 @@ FB_EXPORT int fb_s2_resample_host(const float *lam_field, int64_t lam_w, int64_t
     return FB_OK;
 }
 
-FB_EXPORT int fb_barnes_s2_host(int64_t nsamples, const double *pts, const double *val, const double *sigma,
-                                const double *x0, const double *step, const int64_t *size, int num_iter,
-                                double max_dist_weight, const double *proj, float *res)
+FB_EXPORT int fb_barnes_s2_map_host(int64_t nsamples, const double *pts, const double *val, const double *sigma,
+                                    const double *x0, const double *step, const int64_t *size, int num_iter,
+                                    double max_dist_weight, const fb_s2_map *map, float *res)
 {
     int rc = require_device();
     if (rc != FB_OK) return rc;
-    if (!pts || !val || !sigma || !x0 || !step || !size || !proj || !res) return fail(FB_EINVAL, "null pointer");
+    if (!pts || !val || !sigma || !x0 || !step || !size || !res) return fail(FB_EINVAL, "null pointer");
+    if ((rc = check_map(map)) != FB_OK) return rc;
+    const double *proj = map->proj;
     fb_problem lp;
-    s2_problem(lp, sigma, step, num_iter, max_dist_weight);
+    s2_problem(lp, sigma, step, num_iter, max_dist_weight, *map);
     Derived d;
     if ((rc = derive(&lp, d)) != FB_OK) return rc;
     std::lock_guard<std::mutex> lock(g_arena_mutex);
@@ -1727,6 +1763,18 @@ FB_EXPORT int fb_barnes_s2_host(int64_t nsamples, const double *pts, const doubl
     CUDA_TRY(cudaMemcpyAsync(res, d_res, no * 4, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     return FB_OK;
+}
+
+FB_EXPORT int fb_barnes_s2_host(int64_t nsamples, const double *pts, const double *val, const double *sigma,
+                                const double *x0, const double *step, const int64_t *size, int num_iter,
+                                double max_dist_weight, const double *proj, float *res)
+{
+    if (!proj) return fail(FB_EINVAL, "null pointer");
+    fb_s2_map map;
+    int rc = fb_s2_default_map(&map);
+    if (rc != FB_OK) return rc;
+    memcpy(map.proj, proj, sizeof map.proj);
+    return fb_barnes_s2_map_host(nsamples, pts, val, sigma, x0, step, size, num_iter, max_dist_weight, &map, res);
 }
 
 // ---- introspection ------------------------------------------------------------------------------------------

@@ -34,6 +34,11 @@ class FbProblem(ctypes.Structure):
                 ('max_dist_weight', ctypes.c_double)]
 
 
+class FbS2Map(ctypes.Structure):
+    """ struct fb_s2_map (include/fastbarnes_b200.h). """
+    _fields_ = [('proj', ctypes.c_double * 5), ('lam_x0', ctypes.c_double * 2), ('lam_extent', ctypes.c_double * 2)]
+
+
 # every symbol include/fastbarnes_b200.h declares: name -> (restype, argtypes)
 SIGNATURES = {
     'fb_last_error': (ctypes.c_char_p, []),
@@ -79,6 +84,12 @@ SIGNATURES = {
     'fb_barnes_s2_host': (ctypes.c_int, [ctypes.c_int64, c_double_p, c_double_p, c_double_p, c_double_p,
                                          c_double_p, c_i64_p, ctypes.c_int, ctypes.c_double, c_double_p,
                                          c_float_p]),
+    'fb_s2_default_map': (ctypes.c_int, [ctypes.POINTER(FbS2Map)]),
+    'fb_s2_part1_map_host': (ctypes.c_int, [ctypes.c_int64, c_double_p, c_double_p, c_double_p, c_double_p,
+                                            ctypes.c_int, ctypes.c_double, ctypes.POINTER(FbS2Map), c_float_p]),
+    'fb_barnes_s2_map_host': (ctypes.c_int, [ctypes.c_int64, c_double_p, c_double_p, c_double_p, c_double_p,
+                                             c_double_p, c_i64_p, ctypes.c_int, ctypes.c_double,
+                                             ctypes.POINTER(FbS2Map), c_float_p]),
     'fb_set_option': (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int]),
     'fb_kernel_launch_count': (ctypes.c_int64, []),
     'fb_set_profiling': (ctypes.c_int, [ctypes.c_int]),

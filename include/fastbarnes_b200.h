@@ -179,6 +179,25 @@ int fb_barnes_s2_host(int64_t nsamples, const double *pts, const double *val, co
                       const double *x0, const double *step, const int64_t *size, int num_iter,
                       double max_dist_weight, const double *proj, float *res);
 
+/* Generalised S2 ("next" row N4): the reference hard-codes its Lambert map (interpolationS2.py:187-188
+ * lam_x0 = (-32, -2), extent 64 x 44 map degrees; :208 projection centre (11.5, 34.5), standard
+ * parallels 42.5 / 65.5).  fb_s2_map makes projection and map window arguments; the *_map entry
+ * points run the same three steps on it.  Output pixels whose bilinear stencil leaves the map
+ * window become NaN.                                                                          */
+typedef struct fb_s2_map {
+    double proj[5];         /* fb_lambert_create_proj: (center_lon, n, n_inv, F, rho0) */
+    double lam_x0[2];       /* start of the grid in map coordinates (degrees) */
+    double lam_extent[2];   /* extent of the grid in map degrees; lam_size = (int)(extent / step) */
+} fb_s2_map;
+/* the reference's fixed map */
+int fb_s2_default_map(fb_s2_map *map);
+int fb_s2_part1_map_host(int64_t nsamples, const double *pts, const double *val, const double *sigma,
+                         const double *step, int num_iter, double max_dist_weight, const fb_s2_map *map,
+                         float *lam_field);
+int fb_barnes_s2_map_host(int64_t nsamples, const double *pts, const double *val, const double *sigma,
+                          const double *x0, const double *step, const int64_t *size, int num_iter,
+                          double max_dist_weight, const fb_s2_map *map, float *res);
+
 /* ---- tuning ------------------------------------------------------------------------------- */
 /* process-wide tuning switches that never change results (bit-identical either way):
  *   "two_warp_sweeps" (default 1): sweep launches that fuse >= 2 passes use two warps per 16 lines

@@ -15,6 +15,10 @@ Fixtures (all inputs seeded, outputs produced by the reference's own functions):
   exact_methods.npz 'naive', 'radius' and 'naive_S2' (the exact Gaussian sums) on small seeded
                     cases and on the paper's samples at a coarse grid
                     (only this one:  python oracle/gen_golden.py exact)
+  s2_map_na.npz     the S2 pipeline composed from the reference's own functions (to_map,
+                    _interpolate_opt_convol, _resample) on a user-chosen Lambert map over North
+                    America instead of the hard-coded European one
+                    (only this one:  python oracle/gen_golden.py s2map)
 """
 import hashlib
 import os
@@ -231,9 +235,46 @@ def exact_cases():
     np.savez_compressed(os.path.join(OUT, 'exact_methods.npz'), **d)
 
 
+def s2_map_case():
+    """ Generalised S2 ("next" row N4): interpolationS2.py:180-202 replayed with another projection
+    and map window, using only the reference's functions. """
+    rng = np.random.default_rng(777)
+    n = 1500
+    pts = np.column_stack([rng.uniform(-128.0, -66.0, n), rng.uniform(23.0, 52.0, n)])
+    val = 1013.0 + 8.0 * np.sin(pts[:, 0] / 9.0) + 5.0 * np.cos(pts[:, 1] / 5.0) + rng.normal(0, 0.5, n)
+    step = np.full(2, 0.25)
+    x0 = np.asarray([-125.0, 25.0])
+    size = (220, 100)
+    sigma = np.full(2, 1.0)
+    num_iter = 4
+    mdw = exp(-3.5 ** 2 / 2)
+    proj = reflc.create_proj(-97.625, 37.375, 29.125, 45.625)
+    lons = x0[0] + np.arange(size[0]) * step[0]
+    lats = x0[1] + np.arange(size[1]) * step[1]
+    border = np.concatenate([np.column_stack([lons, np.full(size[0], lats[0])]),
+                             np.column_stack([lons, np.full(size[0], lats[-1])]),
+                             np.column_stack([np.full(size[1], lons[0]), lats]),
+                             np.column_stack([np.full(size[1], lons[-1]), lats])])
+    mapped = reflc.to_map(border, border.copy(), *proj)
+    lam_x0 = np.floor(mapped.min(axis=0) - 4.0)
+    lam_extent = np.ceil(mapped.max(axis=0) + 4.0) - lam_x0
+    lam_size = (int(lam_extent[0] / step[0]), int(lam_extent[1] / step[1]))
+    lam_pts = reflc.to_map(pts, pts.copy(), *proj)
+    v = val.copy()
+    lam = ref._interpolate_opt_convol(lam_pts, v, sigma, lam_x0, step, lam_size, num_iter, mdw)
+    out = refS2._resample(lam, lam_x0, x0, step, size, *proj)
+    np.savez_compressed(os.path.join(OUT, 's2_map_na.npz'), pts=pts, val=val, x0=x0, step=step,
+                        size=np.asarray(size), sigma=sigma, num_iter=num_iter, proj=np.asarray(proj),
+                        lam_x0=lam_x0, lam_extent=lam_extent, lam_pts=lam_pts, lam=lam, out=out)
+    print('s2 map', lam.shape, out.shape, lam_x0, lam_extent, np.isnan(out).mean(), np.isnan(lam).mean())
+
+
 if __name__ == '__main__':
     if len(sys.argv) > 1 and sys.argv[1] == 'exact':
         exact_cases()
+    elif len(sys.argv) > 1 and sys.argv[1] == 's2map':
+        s2_map_case()
     else:
         main()
         exact_cases()
+        s2_map_case()

@@ -295,11 +295,17 @@ def _resample(lam_field, lam_x0, x0, step, size, center_lon, n, n_inv, F, rho0, 
     return res
 
 
-def interpolate_opt_convol_S2_part1(pts, val, sigma, x0, step, size, num_iter, max_dist_weight, nthreads=1):
-    """ fastbarnes/interpolationS2.py:180-196. """
-    lambert_proj = get_lambert_proj()
-    lam_x0 = np.asarray([-32.0, -2.0])
-    lam_size = (int(64.0 / step[0]), int(44.0 / step[1]))
+def interpolate_opt_convol_S2_part1(pts, val, sigma, x0, step, size, num_iter, max_dist_weight, nthreads=1,
+                                    lambert_map=None):
+    """ fastbarnes/interpolationS2.py:180-196.  val is centred in place like in the reference.
+    lambert_map = (proj, lam_x0, lam_extent) replaces the hard-coded map of :187-188, :208. """
+    if lambert_map is None:
+        lambert_proj, lam_x0, lam_extent = get_lambert_proj(), (-32.0, -2.0), (64.0, 44.0)
+    else:
+        lambert_proj, lam_x0, lam_extent = lambert_map
+        lambert_proj = tuple(float(p) for p in lambert_proj)
+    lam_x0 = np.asarray(lam_x0, dtype=np.float64)
+    lam_size = (int(lam_extent[0] / step[0]), int(lam_extent[1] / step[1]))
     pts = np.ascontiguousarray(pts, dtype=np.float64)
     lam_pts = to_map(pts, pts.copy(), *lambert_proj)
     lam_field = _interpolate_opt_convol(lam_pts, val, sigma, lam_x0, step, lam_size, num_iter,
@@ -313,7 +319,7 @@ def interpolate_opt_convol_S2_part2(lam_field, lam_x0, x0, step, size, lambert_p
 
 
 def barnes_S2(pts, val, sigma, x0, step, size, method='optimized_convolution_S2', num_iter=4, max_dist=3.5,
-              resample=True, nthreads=1):
+              resample=True, nthreads=1, lambert_map=None):
     """ fastbarnes/interpolationS2.py:32-138. """
     val = np.array(val, dtype=np.float64, copy=True)
     if method == 'naive_S2':
@@ -323,7 +329,7 @@ def barnes_S2(pts, val, sigma, x0, step, size, method='optimized_convolution_S2'
         raise RuntimeError("encountered invalid Barnes interpolation method: " + str(method))
     res1 = interpolate_opt_convol_S2_part1(pts, val, _vec(sigma, 2), _vec(x0, 2), _vec(step, 2),
                                            tuple(int(s) for s in size), num_iter,
-                                           exp(-max_dist ** 2 / 2), nthreads=nthreads)
+                                           exp(-max_dist ** 2 / 2), nthreads=nthreads, lambert_map=lambert_map)
     if resample:
         return interpolate_opt_convol_S2_part2(*res1, nthreads=nthreads)
     return res1[0]

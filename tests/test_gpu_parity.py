@@ -549,6 +549,51 @@ def test_s2_res64_vs_oracle(fbS2, orc):
     assert np.mean(out[m] != ref[m]) < 0.01
 
 
+def test_s2_user_map(fbS2, orc):
+    """ generalised S2: a user-chosen Lambert map (North America) against the fixture composed
+    from the reference's own functions, and the automatic map against the oracle run on the same map """
+    g = load_golden('s2_map_na')
+    size = tuple(int(s) for s in g['size'])
+    n = int(g['num_iter'])
+    lmap = fbS2.LambertMap(g['proj'], g['lam_x0'], g['lam_extent'])
+    out = fbS2.barnes_S2(g['pts'], g['val'], g['sigma'], g['x0'], g['step'], size, method='optimized_convolution_S2',
+                         num_iter=n, lambert_map=lmap)
+    lam = fbS2.barnes_S2(g['pts'], g['val'], g['sigma'], g['x0'], g['step'], size, method='optimized_convolution_S2',
+                         num_iter=n, resample=False, lambert_map=lmap)
+    for a, b in ((out, g['out']), (lam, g['lam'])):
+        assert a.shape == b.shape and a.dtype == np.float32
+        assert np.array_equal(np.isnan(a), np.isnan(b))
+        m = ~np.isnan(b)
+        assert np.max(np.abs(a[m] - b[m]) / np.abs(b[m])) <= S2_RTOL
+        assert np.mean(a[m] != b[m]) < 0.01
+    # the default map is the reference's
+    d = fbS2.LambertMap.default()
+    assert d.proj == tuple(fbS2.get_lambert_proj()) and d.lam_x0 == (-32.0, -2.0) and d.lam_extent == (64.0, 44.0)
+    # automatic map: window covers the target grid (no NaN from leaving the window where the oracle has data)
+    auto = fbS2.LambertMap.for_grid(g['x0'], g['step'], size, margin=3.5)
+    out_a = fbS2.barnes_S2(g['pts'], g['val'], g['sigma'], g['x0'], g['step'], size, method='optimized_convolution_S2',
+                           num_iter=n, lambert_map=auto)
+    ref_a = orc.barnes_S2(g['pts'], g['val'], g['sigma'], g['x0'], g['step'], size, num_iter=n, nthreads=4,
+                          lambert_map=(auto.proj, auto.lam_x0, auto.lam_extent))
+    assert np.array_equal(np.isnan(out_a), np.isnan(ref_a))
+    m = ~np.isnan(ref_a)
+    assert m.mean() > 0.95
+    assert np.max(np.abs(out_a[m] - ref_a[m]) / np.abs(ref_a[m])) <= S2_RTOL
+    out_s = fbS2.barnes_S2(g['pts'], g['val'], g['sigma'], g['x0'], g['step'], size, method='optimized_convolution_S2',
+                           num_iter=n, lambert_map='auto')
+    assert bits_equal(out_s, out_a)
+    # two maps of the same region give nearly the same field (conformal maps, sigma small against the domain)
+    both = m & ~np.isnan(out)
+    assert np.sqrt(np.mean((out_a[both] - out[both]) ** 2)) < 0.1
+    # a window that does not cover the grid gives NaN outside instead of reading out of bounds
+    small = fbS2.LambertMap(g['proj'], (-10.0, -5.0), (20.0, 10.0))
+    out_w = fbS2.barnes_S2(g['pts'], g['val'], g['sigma'], g['x0'], g['step'], size, method='optimized_convolution_S2',
+                           num_iter=n, lambert_map=small)
+    assert 0.5 < np.isnan(out_w).mean() < 1.0
+    with pytest.raises(RuntimeError):
+        fbS2.barnes_S2(g['pts'], g['val'], g['sigma'], g['x0'], g['step'], size, lambert_map='nope')
+
+
 def test_nan_and_constant_values(fb):
     """ np.amin/np.amax propagate NaN: one NaN observation makes the whole field NaN (reference
     behaviour of _normalize_values); identical observations give offset == value and 0/w + value """

@@ -139,6 +139,20 @@ def test_golden_s2():
     assert bits_equal(out, g['out']) and bits_equal(lam, g['lam'])
 
 
+def test_golden_s2_user_map():
+    # generalised S2: the reference's own to_map / _interpolate_opt_convol / _resample composed
+    # on a North-America Lambert map (oracle/gen_golden.py s2_map_case) vs the oracle with the same map
+    g = load_golden('s2_map_na')
+    size = tuple(int(s) for s in g['size'])
+    lmap = (g['proj'], g['lam_x0'], g['lam_extent'])
+    assert bits_equal(np.asarray(orc.create_proj(-97.625, 37.375, 29.125, 45.625)), g['proj'])
+    out = orc.barnes_S2(g['pts'], g['val'], g['sigma'], g['x0'], g['step'], size, num_iter=int(g['num_iter']),
+                        nthreads=2, lambert_map=lmap)
+    lam = orc.barnes_S2(g['pts'], g['val'], g['sigma'], g['x0'], g['step'], size, num_iter=int(g['num_iter']),
+                        resample=False, nthreads=2, lambert_map=lmap)
+    assert bits_equal(lam, g['lam']) and bits_equal(out, g['out'])
+
+
 EXACT_CASES = [  # name, method, S2
     ('naive_2d', 'naive', False), ('naive_2d_aniso', 'naive', False), ('radius_2d', 'radius', False),
     ('radius_2d_sparse', 'radius', False), ('radius_2d_minw', 'radius', False), ('naive_1d', 'naive', False),
