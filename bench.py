@@ -262,6 +262,33 @@ def run_gpu(args, rank, local_rank, world):
     L.fb_set_profiling(0)
     clocks = sampler.stop(t_begin, t_end)
 
+    # ---- secondary: the same batches in fp32 working precision (north_star's fp32 path; not the headline,
+    # the reference computes in fp64) ----------------------------------------------------------------
+    fp32 = None
+    if not args.no_fp32:
+        plans32 = [fbi.BarnesDevice(2, SIGMA, X0, STEP, SIZE, nfields=F, nsamples=F * N_PER_FIELD, num_iter=NUM_ITER,
+                                    device=dev, precision='fp32') for _ in range(nstreams)]
+        plans64, plans[:] = list(plans), plans32
+        run_steps(args.warmup)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        run_steps(args.steps)
+        e1.record()
+        barrier()
+        ms32 = e0.elapsed_time(e1)
+        L.fb_set_profiling(1)
+        seg32 = np.zeros(5)
+        for _ in range(args.steps):
+            plans32[0](d_pts, d_val)
+            _lib.check(L.fb_last_profile(seg.ctypes.data_as(_lib.c_double_p), 5, nl.ctypes.data_as(_lib.c_i64_p)))
+            seg32 += seg
+        seg32 /= args.steps
+        L.fb_set_profiling(0)
+        plans[:] = plans64
+        fp32 = (ms32, seg32)
+        del plans32
+
     # ---- end-to-end arm: host buffers through the C ABI -----------------------------------------------
     out_pin = torch.empty((F,) + SIZE[::-1], dtype=torch.float32).pin_memory()
     prob = plan.prob
@@ -283,10 +310,10 @@ def run_gpu(args, rank, local_rank, world):
     e2e_s = time.perf_counter() - t0
 
     # ---- reduce over ranks (max time) ------------------------------------------------------------------
-    t = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms_total, e2e_s * 1e3, fp32[0] if fp32 else 0.0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, e2e_ms = float(t[0]), float(t[1])
+    ms_total, e2e_ms, ms32_total = float(t[0]), float(t[1]), float(t[2])
     if rank == 0:
         pts_per_step = F * POINTS_PER_FIELD * world
         value = pts_per_step * args.steps / (ms_total * 1e-3)
@@ -336,6 +363,18 @@ def run_gpu(args, rank, local_rank, world):
             },
             'clocks': clocks,
         }
+        if fp32:
+            s32 = fp32[1]
+            bx, by = 16, 12     # fp32 sweeps: x reads and writes float2 nodes (8 + 8 B); y reads 8 B, writes the float32 field (4 B)
+            line['fp32_path'] = {
+                'note': 'same batches with FB_FLAG_FP32 (sweeps in fp32 working precision, tolerance-level parity); secondary number',
+                'value': pts_per_step * args.steps / (ms32_total * 1e-3), 'unit': UNIT, 'ms_per_step': ms32_total / args.steps,
+                'ms_zero_fill': float(s32[0]), 'ms_minmax_inject': float(s32[1]), 'ms_sweep_x': float(s32[2]),
+                'ms_sweep_y': float(s32[3]),
+                'sweep_x_GBps': bx * pts_launch / (s32[2] * 1e-3) / 1e9 if s32[2] > 0 else 0.0,
+                'sweep_y_GBps': by * pts_launch / (s32[3] * 1e-3) / 1e9 if s32[3] > 0 else 0.0,
+                'sweep_x_frac_of_peak': bx * pts_launch / (s32[2] * 1e-3) / 1e9 / peak if s32[2] > 0 else 0.0,
+                'sweep_y_frac_of_peak': by * pts_launch / (s32[3] * 1e-3) / 1e9 / peak if s32[3] > 0 else 0.0}
         if world == 1 and not args.no_cpu:
             cores = os.cpu_count() or 1
             nf = max(cores, 8) * 2
@@ -358,6 +397,7 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--streams', type=int, default=2, help='device-resident arm: batches alternate over this many streams')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--no-fp32', action='store_true', help='skip the secondary fp32 working-precision measurement')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))

@@ -8,6 +8,7 @@
 #include "../../include/fastbarnes_b200.h"
 #include "fb_kernels.cuh"
 #include "fb_exact.cuh"
+#include "fb_sweep32.cuh"
 
 #include <atomic>
 #include <cmath>
@@ -393,6 +394,93 @@ int launch_sweeph(int m, int npass, const FbSweep &p, cudaStream_t st)
     return launch_sweeph_m<2>(npass, p, st);
 }
 
+// ---- fp32 working precision (FB_FLAG_FP32): fb_sweep32_kernel ------------------------------------------------
+inline int sweep32_ring_depth(int D) { return (D + FB_SWEEP_U + FB_SWEEP_U - 1) / FB_SWEEP_U * FB_SWEEP_U; }
+inline int sweep32_tmem_cols(int npass, int D)
+{
+    const int nt = npass > 2 ? npass - 2 : 0;
+    if (nt == 0) return 0;
+    int need = nt * sweep32_ring_depth(D) * 2, cols = 32;
+    while (cols < need) cols *= 2;
+    return cols;
+}
+inline size_t sweep32_smem_bytes(int npass, int mode, int D)
+{
+    size_t words = npass > 1 ? (size_t)sweep32_ring_depth(D) * 32 : 0;
+    if (mode == 1) words += (size_t)FB32_TILE_K * FB32_TILE_PITCH;
+    return 4 * words * sizeof(unsigned long long);
+}
+// all passes of an axis run in one launch: batched ring reads need D >= U, the rings must fit on chip
+inline bool sweep32_fits(int npass, int D)
+{
+    return npass >= 1 && npass <= FB_MAX_FUSED_PASSES && D >= FB_SWEEP_U && sweep32_tmem_cols(npass, D) <= 512 &&
+           sweep32_smem_bytes(npass, 1, D) + 1024 <= kSmemLimit;
+}
+
+template <int NPASS, int MODE>
+int launch_sweep32_t(FbSweep32 p, cudaStream_t st)
+{
+    static thread_local size_t configured[16] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const size_t smem = sweep32_smem_bytes(NPASS, MODE, p.D);
+    if (smem > 40 * 1024 && configured[dev & 15] < smem) {
+        CUDA_TRY(cudaFuncSetAttribute(fb_sweep32_kernel<NPASS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+        CUDA_TRY(cudaFuncSetAttribute(fb_sweep32_kernel<NPASS, MODE>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                      cudaSharedmemCarveoutMaxShared));
+        configured[dev & 15] = kSmemLimit;
+    }
+    const long long nitems = p.n_outer * p.n_groups;
+    if (nitems <= 0) return FB_OK;
+    p.tmem_cols = sweep32_tmem_cols(NPASS, p.D);
+    int per_sm = 2;                                          // launch bounds: 2 CTAs of 128 threads
+    if ((int)(kSmemPerSM / (smem + 1024)) < per_sm) per_sm = (int)(kSmemPerSM / (smem + 1024));
+    if (p.tmem_cols > 0 && per_sm * p.tmem_cols > 512) per_sm = 512 / p.tmem_cols;
+    if (per_sm < 1) per_sm = 1;
+    long long grid = (long long)per_sm * sm_count(dev);
+    if (grid > (nitems + 3) / 4) grid = (nitems + 3) / 4;
+    if (getenv("FB_DEBUG")) fprintf(stderr, "[fb] sweep32<%d,%d> smem %zu tmem_cols %d per_sm %d grid %lld items %lld\n", NPASS, MODE, smem, p.tmem_cols, per_sm, grid, nitems);
+    CUDA_TRY(cudaMemsetAsync(p.work_counter, 0, sizeof(unsigned long long), st));
+    fb_sweep32_kernel<NPASS, MODE><<<(unsigned)grid, 128, smem, st>>>(p);
+    LAUNCH_CHECK();
+    return FB_OK;
+}
+
+template <int MODE>
+int launch_sweep32_m(int npass, const FbSweep32 &p, cudaStream_t st)
+{
+    switch (npass) {
+    case 1: return launch_sweep32_t<1, MODE>(p, st);
+    case 2: return launch_sweep32_t<2, MODE>(p, st);
+    case 3: return launch_sweep32_t<3, MODE>(p, st);
+    case 4: return launch_sweep32_t<4, MODE>(p, st);
+    case 5: return launch_sweep32_t<5, MODE>(p, st);
+    case 6: return launch_sweep32_t<6, MODE>(p, st);
+    }
+    return fail(FB_EINVAL, "unsupported number of fused passes: %d", npass);
+}
+
+// one axis of the fp32 path
+int run_sweep32(int mode, int num_iter, const AxisParams &ax, const fb_f2 *src2, fb_f2 *dst2, float *out32, const unsigned long long *mm, double csf, long long n_outer, long long L,
+                long long n_inner, cudaStream_t st, SweepCounters &ctr)
+{
+    const int D = 2 * ax.T + 2;
+    if (!sweep32_fits(num_iter, D))
+        return fail(FB_EKERNEL, "the fp32 path does not cover this kernel (T=%d, num_iter=%d: needs 3 <= T and on-chip rings); "
+                                "use the fp64 path", ax.T, num_iter);
+    if ((L + (FB_L2_PREFETCH_CHUNKS + 2) * FB_SWEEP_U) * n_inner > 2147483647LL)
+        return fail(FB_EINVAL, "the fp32 path addresses a line with 32-bit element offsets: L * n_inner too large");
+    FbSweep32 p{};
+    p.in2 = src2; p.out2 = dst2; p.out32 = out32; p.mm = mm;
+    p.n_outer = n_outer; p.L = L; p.n_inner = n_inner; p.n_groups = (n_inner + 31) / 32;
+    p.T = ax.T; p.D = D; p.R = sweep32_ring_depth(D);
+    p.alpha = (float)ax.alpha; p.csf = (float)csf;
+    p.work_counter = ctr.base + (ctr.next++ % kSweepCounterSlots);
+    if (mode == 0) return launch_sweep32_m<0>(num_iter, p, st);
+    if (mode == 1) return launch_sweep32_m<1>(num_iter, p, st);
+    return launch_sweep32_m<2>(num_iter, p, st);
+}
+
 // tensor-memory kernel: 4 warps per CTA, one CTA per SM (it allocates all 512 TMEM columns)
 inline bool sweep_tmem_fits(int npass, int D)
 {
@@ -748,18 +836,19 @@ int check_offsets(const fb_problem *pr, long long nsamples, const int64_t *off, 
 // z_off / z_cnt: z window of the injected buffers (z-slab runs); the whole grid is (0, d.Dz).
 int run_inject(const fb_problem *pr, const Derived &d, long long nsamples, const int64_t *h_offsets,
                const double *d_pts, const double *d_val, Workspace &w, cudaStream_t st,
-               long long z_off = 0, long long z_cnt = -1)
+               long long z_off = 0, long long z_cnt = -1, bool f32 = false)
 {
+    // f32: the injected grid is ONE array of interleaved float2 (value, weight) nodes in w.vA (fp32 path)
     if (z_cnt < 0) z_cnt = d.Dz;
     const long long slab_total = d.W * d.H * z_cnt;
     long long max_n = 0;
     int rc = check_offsets(pr, nsamples, h_offsets, max_n);
     if (rc != FB_OK) return rc;
     if (max_n > 2147483647LL) return fail(FB_EINVAL, "too many samples in one field");
-    if ((nsamples << pr->dim) > 4294967295LL) return fail(FB_EINVAL, "too many sample records");
+    if ((nsamples << pr->dim) > (f32 ? 2147483647LL : 4294967295LL)) return fail(FB_EINVAL, "too many sample records");
     const size_t g = (size_t)pr->nfields * (size_t)slab_total * sizeof(double);
     CUDA_TRY(cudaMemsetAsync(w.vA, 0, g, st));
-    CUDA_TRY(cudaMemsetAsync(w.wA, 0, g, st));
+    if (!f32) CUDA_TRY(cudaMemsetAsync(w.wA, 0, g, st));
     fb_init_kernel<<<(unsigned)((pr->nfields + 255) / 256), 256, 0, st>>>(w.mm, pr->nfields, w.counters);
     LAUNCH_CHECK();
     {
@@ -790,17 +879,28 @@ int run_inject(const fb_problem *pr, const Derived &d, long long nsamples, const
     fb_minmax_kernel<<<dim3((unsigned)mmb, nf), 256, 0, st>>>(s, w.mm);
     LAUNCH_CHECK();
     const dim3 sg((unsigned)((max_n + 255) / 256), nf);
-    fb_inject_count_kernel<<<sg, 256, 0, st>>>(s, gr, w.vA, w.wA, w.first_mask);
-    LAUNCH_CHECK();
-    fb_inject_alloc_kernel<<<sg, 256, 0, st>>>(s, gr, w.vA, w.wA, w.first_mask, w.counters, w.seg_node, w.seg_base, w.seg_n);
-    LAUNCH_CHECK();
-    fb_inject_place_kernel<<<sg, 256, 0, st>>>(s, gr, w.vA, w.wA, w.mm, w.rec_k, w.rec_w, w.rec_wv);
-    LAUNCH_CHECK();
     const long long R = nsamples << pr->dim;
     long long rblocks = (R + 127) / 128;
     if (rblocks > 148 * 16) rblocks = 148 * 16;
-    fb_inject_reduce_kernel<<<(unsigned)rblocks, 128, 0, st>>>(w.counters, w.seg_node, w.seg_base, w.seg_n,
-                                                                        w.rec_k, w.rec_w, w.rec_wv, w.vA, w.wA);
+    if (f32) {
+        fb_inject_count_kernel<true><<<sg, 256, 0, st>>>(s, gr, w.vA, w.wA, w.first_mask);
+        LAUNCH_CHECK();
+        fb_inject_alloc_kernel<true><<<sg, 256, 0, st>>>(s, gr, w.vA, w.wA, w.first_mask, w.counters, w.seg_node, w.seg_base, w.seg_n);
+        LAUNCH_CHECK();
+        fb_inject_place_kernel<true><<<sg, 256, 0, st>>>(s, gr, w.vA, w.wA, w.mm, w.rec_k, w.rec_w, w.rec_wv);
+        LAUNCH_CHECK();
+        fb_inject_reduce_kernel<true><<<(unsigned)rblocks, 128, 0, st>>>(w.counters, w.seg_node, w.seg_base, w.seg_n,
+                                                                               w.rec_k, w.rec_w, w.rec_wv, w.vA, w.wA);
+    } else {
+        fb_inject_count_kernel<false><<<sg, 256, 0, st>>>(s, gr, w.vA, w.wA, w.first_mask);
+        LAUNCH_CHECK();
+        fb_inject_alloc_kernel<false><<<sg, 256, 0, st>>>(s, gr, w.vA, w.wA, w.first_mask, w.counters, w.seg_node, w.seg_base, w.seg_n);
+        LAUNCH_CHECK();
+        fb_inject_place_kernel<false><<<sg, 256, 0, st>>>(s, gr, w.vA, w.wA, w.mm, w.rec_k, w.rec_w, w.rec_wv);
+        LAUNCH_CHECK();
+        fb_inject_reduce_kernel<false><<<(unsigned)rblocks, 128, 0, st>>>(w.counters, w.seg_node, w.seg_base, w.seg_n,
+                                                                                w.rec_k, w.rec_w, w.rec_wv, w.vA, w.wA);
+    }
     LAUNCH_CHECK();
     return FB_OK;
 }
@@ -832,6 +932,26 @@ int run_sweeps(const fb_problem *pr, const Derived &d, Workspace &w, float *d_ou
         rc = run_sweep(2, n, d.ax[0], cur, spare, d_out, d_out64, w.mm, d.csf, nf, d.W, 1, true, st, ctr);
         if (rc != FB_OK) return rc;
         return prof_mark(3, st);
+    }
+    if (pr->flags & FB_FLAG_FP32) {
+        // fp32 working precision: the B buffers hold interleaved float2 (value, weight) nodes
+        const fb_f2 *a2 = reinterpret_cast<const fb_f2 *>(w.vA);     // injected float2 nodes, [..][x][y]
+        fb_f2 *b2 = reinterpret_cast<fb_f2 *>(w.vB);
+        rc = run_sweep32(1, n, d.ax[0], a2, b2, nullptr, w.mm, d.csf, nf * d.Dz, d.W, d.H, st, ctr);
+        if (rc != FB_OK) return rc;
+        if ((rc = prof_mark(3, st)) != FB_OK) return rc;
+        if (pr->dim == 2) {
+            rc = run_sweep32(2, n, d.ax[1], b2, nullptr, d_out, w.mm, d.csf, nf, d.H, d.W, st, ctr);
+            if (rc != FB_OK) return rc;
+            return prof_mark(4, st);
+        }
+        fb_f2 *c2 = reinterpret_cast<fb_f2 *>(w.wB);
+        rc = run_sweep32(0, n, d.ax[1], b2, c2, nullptr, w.mm, d.csf, nf * d.Dz, d.H, d.W, st, ctr);
+        if (rc != FB_OK) return rc;
+        if ((rc = prof_mark(4, st)) != FB_OK) return rc;
+        rc = run_sweep32(2, n, d.ax[2], c2, nullptr, d_out, w.mm, d.csf, nf, d.Dz, d.H * d.W, st, ctr);
+        if (rc != FB_OK) return rc;
+        return prof_mark(5, st);
     }
     // x sweep: A layout [..][x][y] -> natural layout [..][y][x]
     rc = run_sweep(1, n, d.ax[0], cur, spare, nullptr, nullptr, w.mm, d.csf, nf * d.Dz, d.W, d.H, true, st, ctr);
@@ -871,6 +991,10 @@ int pipeline(const fb_problem *pr, long long nsamples, const int64_t *h_offsets,
         rc = check_kernel_vs_grid(pr, d);
         if (rc != FB_OK) return rc;
     }
+    if (pr->flags & FB_FLAG_FP32) {
+        if (pr->dim < 2) return fail(FB_EINVAL, "the fp32 path covers 2D and 3D grids (a 1D grid is a single line: use the fp64 path)");
+        if (d_out64) return fail(FB_EINVAL, "the fp32 path has no fp64 quotient output");
+    }
     Workspace w;
     const SegPlan sp = seg_plan(pr, d);
     carve(w, (char *)d_ws, pr, d.total, nsamples, &sp);
@@ -878,7 +1002,7 @@ int pipeline(const fb_problem *pr, long long nsamples, const int64_t *h_offsets,
     g_prof.launches_begin = g_launches.load();
     g_prof.marked = 0;
     if ((rc = prof_mark(0, st)) != FB_OK) return rc;
-    rc = run_inject(pr, d, nsamples, h_offsets, d_pts, d_val, w, st);
+    rc = run_inject(pr, d, nsamples, h_offsets, d_pts, d_val, w, st, 0, -1, (pr->flags & FB_FLAG_FP32) != 0);
     if (rc != FB_OK) return rc;
     if ((rc = prof_mark(2, st)) != FB_OK) return rc;
     rc = run_sweeps(pr, d, w, d_out, d_out64, st, sp);

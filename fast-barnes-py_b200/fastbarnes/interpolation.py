@@ -72,6 +72,19 @@ def _check_samples(pts, val):
 
 
 FLAG_SEGMENTED_1D = 1
+FLAG_FP32 = 2
+
+
+def _precision_flag(precision, dim, return_float64=False):
+    if precision == 'fp64':
+        return 0
+    if precision != 'fp32':
+        raise RuntimeError("precision should be 'fp64' or 'fp32': " + str(precision))
+    if dim < 2:
+        raise RuntimeError('fp32 working precision covers 2D and 3D grids only')
+    if return_float64:
+        raise RuntimeError('fp32 working precision has no float64 quotient')
+    return FLAG_FP32
 # 1D grids longer than this are swept in overlapping segments unless exact=True is requested
 SEGMENTED_1D_THRESHOLD = 1 << 16
 
@@ -107,7 +120,7 @@ def _check_kernel_vs_grid(method, sigma, step, size, num_iter):
 # ---------------------------------------------------------------------------------------------
 
 def barnes(pts, val, sigma, x0, step, size, method='optimized_convolution',
-           num_iter=4, max_dist=3.5, min_weight=0.001, *, return_float64=False, exact=None):
+           num_iter=4, max_dist=3.5, min_weight=0.001, *, return_float64=False, exact=None, precision='fp64'):
     """
     Barnes interpolation of the observation values `val` at the sample points `pts` with
     Gaussian width `sigma` on the regular grid (`x0`, `step`, `size`) in 1, 2 or 3 dimensions.
@@ -139,7 +152,7 @@ def barnes(pts, val, sigma, x0, step, size, method='optimized_convolution',
 
     if method in _CONV_METHODS:
         _check_kernel_vs_grid(method, sigma, step, size, num_iter)
-        flags = 0
+        flags = _precision_flag(precision, dim, return_float64)
         if dim == 1 and (exact is False or (exact is None and size[0] > SEGMENTED_1D_THRESHOLD)):
             flags |= FLAG_SEGMENTED_1D
         return _run(pts, val, sigma, x0, step, size, _CONV_METHODS[method], num_iter, max_dist_weight,
@@ -194,14 +207,14 @@ def _run(pts, val, sigma, x0, step, size, method_id, num_iter, max_dist_weight, 
 
 
 def barnes_batched(pts, val, sigma, x0, step, size, sample_offsets=None, method='optimized_convolution',
-                   num_iter=4, max_dist=3.5, *, return_float64=False):
+                   num_iter=4, max_dist=3.5, *, return_float64=False, precision='fp64'):
     """
     Interpolates B independent fields (e.g. time steps or ensemble members) on the same grid
     in one call.  `pts` (sum N_b, M) and `val` (sum N_b,) hold the samples of all fields
     back to back; field b owns rows [sample_offsets[b], sample_offsets[b+1]).  Alternatively
     pass `pts` of shape (B, N, M) and `val` of shape (B, N) with sample_offsets=None.
     Returns a float32 array of shape (B,) + size[::-1]; field b equals
-    `barnes(pts_b, val_b, ...)` bit for bit.
+    `barnes(pts_b, val_b, ...)` bit for bit (also with precision='fp32', see `barnes`).
     """
     if method not in _CONV_METHODS:
         raise RuntimeError("encountered invalid Barnes interpolation method: " + str(method))
@@ -234,7 +247,8 @@ def barnes_batched(pts, val, sigma, x0, step, size, sample_offsets=None, method=
     size = _grid_size(size, dim)
     _check_kernel_vs_grid(method, sigma, step, size, num_iter)
     return _run(pts, val, sigma, x0, step, size, _CONV_METHODS[method], num_iter, exp(-max_dist ** 2 / 2),
-                offsets=sample_offsets, nfields=nfields, return_float64=return_float64)
+                offsets=sample_offsets, nfields=nfields, return_float64=return_float64,
+                flags=_precision_flag(precision, dim, return_float64))
 
 
 # ---------------------------------------------------------------------------------------------
@@ -412,7 +426,7 @@ class BarnesDevice:
     """
 
     def __init__(self, dim, sigma, x0, step, size, nfields, nsamples, method='optimized_convolution',
-                 num_iter=4, max_dist=3.5, sample_offsets=None, device=None, want_float64=False):
+                 num_iter=4, max_dist=3.5, sample_offsets=None, device=None, want_float64=False, precision='fp64'):
         import torch
         if method not in _CONV_METHODS:
             raise RuntimeError("encountered invalid Barnes interpolation method: " + str(method))
@@ -429,7 +443,7 @@ class BarnesDevice:
         self.nfields = int(nfields)
         self.nsamples = int(nsamples)
         self.prob = _problem(dim, sigma, x0, step, self.size, _CONV_METHODS[method], num_iter,
-                             exp(-max_dist ** 2 / 2), nfields)
+                             exp(-max_dist ** 2 / 2), nfields, _precision_flag(precision, dim, want_float64))
         self.offsets = None if sample_offsets is None else np.ascontiguousarray(sample_offsets, dtype=np.int64)
         L = _lib.lib()
         nbytes = L.fb_workspace_bytes(self.prob, self.nsamples)

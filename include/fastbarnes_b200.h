@@ -45,6 +45,13 @@ extern "C" {
                                     swept in parallel (exact in exact arithmetic, rounding-level difference to the
                                     reference's single accumulator chain); default is the bit-exact sequential walk */
 
+#define FB_FLAG_FP32 2            /* dim 2 or 3: fp32 working precision for the sweeps (grid as interleaved float2 (value,
+                                    weight) nodes, packed f32x2 arithmetic with Kahan-compensated accumulators, half the
+                                    HBM traffic).  Injection stays fp64.  Not bit-identical to the reference: |field -
+                                    reference| stays within a few float32 ulps of the field values except next to the
+                                    max_dist boundary (tolerance stated in tests/test_gpu_parity.py); needs
+                                    3 <= T and the rings of all passes on chip (FB_EKERNEL otherwise); no out64 */
+
 #define FB_METHOD_OPTIMIZED_CONVOLUTION 0   /* interpolation.py:169-176 */
 #define FB_METHOD_CONVOLUTION           1   /* interpolation.py:178-185 */
 /* exact Gaussian sums (fb_barnes_exact_*), the reference's accuracy yardsticks */
