@@ -468,7 +468,7 @@ int run_sweep32(int mode, int num_iter, const AxisParams &ax, const fb_f2 *src2,
     if (!sweep32_fits(num_iter, D))
         return fail(FB_EKERNEL, "the fp32 path does not cover this kernel (T=%d, num_iter=%d: needs 3 <= T and on-chip rings); "
                                 "use the fp64 path", ax.T, num_iter);
-    if ((L + (FB_L2_PREFETCH_CHUNKS + 2) * FB_SWEEP_U) * n_inner > 2147483647LL)
+    if ((L + (FB32_L2_PREFETCH_CHUNKS + 2) * FB_SWEEP_U) * n_inner * 8 > 4294967295LL)
         return fail(FB_EINVAL, "the fp32 path addresses a line with 32-bit element offsets: L * n_inner too large");
     FbSweep32 p{};
     p.in2 = src2; p.out2 = dst2; p.out32 = out32; p.mm = mm;

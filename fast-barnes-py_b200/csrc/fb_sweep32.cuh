@@ -66,6 +66,20 @@ __device__ __forceinline__ T *fb_row(T *base, unsigned j, unsigned stride_bytes)
     return reinterpret_cast<T *>(r);
 }
 
+// the address arithmetic above hides the address space from the compiler: state it in the access
+__device__ __forceinline__ fb_f2 fb_ldg2(const fb_f2 *q)
+{
+    fb_f2 r;
+    asm("ld.global.nc.b64 %0, [%1];" : "=l"(r) : "l"(q));
+    return r;
+}
+__device__ __forceinline__ void fb_stg2(fb_f2 *q, fb_f2 v) { asm volatile("st.global.b64 [%0], %1;" ::"l"(q), "l"(v) : "memory"); }
+__device__ __forceinline__ void fb_stg1(float *q, float v) { asm volatile("st.global.f32 [%0], %1;" ::"l"(q), "f"(v) : "memory"); }
+
+#ifndef FB32_L2_PREFETCH_CHUNKS
+#define FB32_L2_PREFETCH_CHUNKS 5
+#endif
+
 struct FbSweep32 {
     const fb_f2 *in2;               // [outer][k][inner]
     fb_f2 *out2;                    // MODE 0 / 1
@@ -78,7 +92,9 @@ struct FbSweep32 {
     int tmem_cols;                  // tensor-memory columns per CTA (0: none needed)
 };
 
-#define FB32_TILE_K 16
+#ifndef FB32_TILE_K
+#define FB32_TILE_K 32      // k extent of the transposing tile: a line receives runs of 256 bytes
+#endif
 #define FB32_TILE_PITCH 33
 
 // The U = 8 steps of one chunk for all passes.  ring: this lane's shared-memory ring of pass 2
@@ -236,12 +252,14 @@ fb_sweep32_kernel(const FbSweep32 p)
     };
     // byte offsets inside a line fit 32 bits (checked by the launcher): one IMAD.WIDE per address
     const unsigned sk8 = (unsigned)p.n_inner * 8u;
+    // Straight-line loads (no predicate, no branch: a conditional load makes the compiler merge the loaded
+    // registers with MOVs right behind the loads, which stalls the warp for the whole load latency).
+    // Lanes beyond n_inner read the last valid line instead; nothing of theirs is ever stored.
+    const fb_f2 *in_safe = p.in2 + (outer * p.L) * p.n_inner + (active ? inner : p.n_inner - 1);
     auto load_inside = [&](fb_f2 (&r)[U], int t0) {
-        if (active) {
-            const fb_f2 *p0 = fb_row(in, (unsigned)t0, sk8);
+        const fb_f2 *p0 = fb_row(in_safe, (unsigned)t0, sk8);
 #pragma unroll
-            for (int j = 0; j < U; ++j) r[j] = *fb_row(p0, (unsigned)j, sk8);
-        }
+        for (int j = 0; j < U; ++j) r[j] = fb_ldg2(fb_row(p0, (unsigned)j, sk8));
     };
     // L2 prefetch of the rows [t0, t0 + nrows), nrows <= 16, with ONE instruction per warp: lane l takes the
     // 128-byte half (l & 1) of the warp's 256-byte segment of row t0 + (l >> 1)
@@ -257,17 +275,18 @@ fb_sweep32_kernel(const FbSweep32 p)
     // consecutive k of one line (128 B)
     auto flush_tile = [&](int k0, int cnt) {
         __syncwarp();
-        const int kk = lane & 15, half = lane >> 4;
+        constexpr int CPI = 32 / TK;                   // line columns per store instruction
+        const int kk = lane % TK, sub = lane / TK;
         if (full_group && cnt == TK) {
-            const fb_f2 *tp = tile + kk * TP + half;
-            fb_f2 *o = p.out2 + (outer * p.n_inner + group * 32 + half) * p.L + k0 + kk;
-            const unsigned rs8 = (unsigned)p.L * 16u;                 // two lines further, in bytes
+            const fb_f2 *tp = tile + kk * TP + sub;
+            fb_f2 *o = p.out2 + (outer * p.n_inner + group * 32 + sub) * p.L + k0 + kk;
+            const unsigned rs8 = (unsigned)p.L * (8u * CPI);          // CPI lines further, in bytes
 #pragma unroll
-            for (int it = 0; it < 16; ++it) *fb_row(o, (unsigned)it, rs8) = tp[it * 2];
+            for (int it = 0; it < TK; ++it) fb_stg2(fb_row(o, (unsigned)it, rs8), tp[it * CPI]);
         } else {
 #pragma unroll 4
-            for (int it = 0; it < 16; ++it) {
-                const int col = it * 2 + half;
+            for (int it = 0; it < TK; ++it) {
+                const int col = it * CPI + sub;
                 const long long inner_j = group * 32 + col;
                 if (kk < cnt && inner_j < p.n_inner)
                     p.out2[(outer * p.n_inner + inner_j) * p.L + k0 + kk] = tile[kk * TP + col];
@@ -298,7 +317,7 @@ fb_sweep32_kernel(const FbSweep32 p)
             if (active) {
                 fb_f2 *o = fb_row(p.out2 + base, (unsigned)kb, sk8);
 #pragma unroll
-                for (int j = 0; j < U; ++j) *fb_row(o, (unsigned)j, sk8) = xs[j];
+                for (int j = 0; j < U; ++j) fb_stg2(fb_row(o, (unsigned)j, sk8), xs[j]);
             }
         } else if (MODE == 1) {
             const int row0 = kb & (TK - 1);
@@ -311,7 +330,7 @@ fb_sweep32_kernel(const FbSweep32 p)
             if (active) {
                 float *o = fb_row(p.out32 + base, (unsigned)kb, sk8 >> 1);
 #pragma unroll
-                for (int j = 0; j < U; ++j) *fb_row(o, (unsigned)j, sk8 >> 1) = finalize(xs[j]);
+                for (int j = 0; j < U; ++j) fb_stg1(fb_row(o, (unsigned)j, sk8 >> 1), finalize(xs[j]));
             }
         }
     };
@@ -343,7 +362,7 @@ fb_sweep32_kernel(const FbSweep32 p)
             fb_f2 bn[U], bo[U];
 #pragma unroll 1
             for (; t < stop; t += U) {
-                prefetch_l2(t + FB_L2_PREFETCH_CHUNKS * U, U);
+                prefetch_l2(t + FB32_L2_PREFETCH_CHUNKS * U, U);
                 load_ranged(bn, t);
                 load_ranged(bo, t - D);
                 fb_sweep32_chunk<NPASS, U, true>(bn, bo, accu, comp, new0, xs, ring, tring, rslot, wslot, R, t, T1, L, alpha2);
@@ -370,14 +389,22 @@ fb_sweep32_kernel(const FbSweep32 p)
             load_inside(ao, t - D);
 #pragma unroll 1
             for (;;) {
-                prefetch_l2(t + FB_L2_PREFETCH_CHUNKS * U, 2 * U);          // the rows of this and the next chunk
-                if (t + U < t_hi) { load_inside(cn, t + U); load_inside(co, t + U - D); }
+                prefetch_l2(t + FB32_L2_PREFETCH_CHUNKS * U, 2 * U);          // the rows of this and the next chunk
+                {   // the chunk after the last interior one is loaded by the masked code: reload this one instead
+                    const int tn = (t + U < t_hi) ? t + U : t;
+                    load_inside(cn, tn);
+                    load_inside(co, tn - D);
+                }
                 fb_sweep32_chunk<NPASS, U, false>(an, ao, accu, comp, new0, xs, ring, tring, rslot, wslot, R, t, T1, L, alpha2);
                 emit_chunk(xs, t - lag);
                 advance();
                 t += U;
                 if (t >= t_hi) break;
-                if (t + U < t_hi) { load_inside(an, t + U); load_inside(ao, t + U - D); }
+                {
+                    const int tn = (t + U < t_hi) ? t + U : t;
+                    load_inside(an, tn);
+                    load_inside(ao, tn - D);
+                }
                 fb_sweep32_chunk<NPASS, U, false>(cn, co, accu, comp, new0, xs, ring, tring, rslot, wslot, R, t, T1, L, alpha2);
                 emit_chunk(xs, t - lag);
                 advance();
