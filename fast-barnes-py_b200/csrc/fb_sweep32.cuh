@@ -97,34 +97,61 @@ struct FbSweep32 {
 #endif
 #define FB32_TILE_PITCH 33
 
+// volatile: keeps the load where it is written (the interior loop reloads a register right after its use)
+__device__ __forceinline__ fb_f2 fb_ldg2_here(const fb_f2 *q)
+{
+    fb_f2 r;
+    asm volatile("ld.global.nc.b64 %0, [%1];" : "=l"(r) : "l"(q));
+    return r;
+}
+
+// tensor-memory ring reads of the chunk whose first read slot is rslot (issue only; fb_tmem_wait_ld16 later)
+template <int NT, int U>
+__device__ __forceinline__ void fb_sweep32_tmem_issue(unsigned (&oldr)[NT > 0 ? NT : 1][16], unsigned tring, int rslot, int R)
+{
+    if (NT > 0) {
+        if (rslot + U <= R) {
+#pragma unroll
+            for (int q = 0; q < NT; ++q) fb_tmem_ld16(tring + 2u * (unsigned)(q * R + rslot), oldr[q]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < U; ++j) {
+                int rj = rslot + j;
+                rj = (rj >= R) ? rj - R : rj;
+#pragma unroll
+                for (int q = 0; q < NT; ++q) fb_tmem_ld2(tring + 2u * (unsigned)(q * R + rj), oldr[q][2 * j], oldr[q][2 * j + 1]);
+            }
+        }
+    }
+}
+
 // The U = 8 steps of one chunk for all passes.  ring: this lane's shared-memory ring of pass 2
 // (slot s at ring[s * 32]); tring: tensor-memory address of the ring of pass 3, slot 0.
-template <int NPASS, int U, bool MASKED>
+// oldr holds the tensor-memory ring reads of THIS chunk, issued by the caller / the previous chunk.
+// PIPE (interior chunks): every input register is reloaded for the next chunk (row pointers pn, po)
+// right after its use, and the tensor-memory reads of the next chunk are issued at the end, so both
+// latencies overlap a whole chunk of arithmetic without a second set of buffers.
+template <int NPASS, int U, bool MASKED, bool PIPE>
 __device__ __forceinline__ void fb_sweep32_chunk(
-    const fb_f2 (&bn)[U], const fb_f2 (&bo)[U], fb_f2 (&accu)[NPASS], fb_f2 (&comp)[NPASS], fb_f2 (&new0)[NPASS],
-    fb_f2 (&xs)[U], fb_f2 *ring, unsigned tring, int rslot, int wslot, int R, int t, int T1, int L, fb_f2 alpha2)
+    fb_f2 (&bn)[U], fb_f2 (&bo)[U], fb_f2 (&accu)[NPASS], fb_f2 (&comp)[NPASS], fb_f2 (&new0)[NPASS],
+    fb_f2 (&xs)[U], unsigned (&oldr)[(NPASS > 2 ? NPASS - 2 : 0) > 0 ? (NPASS > 2 ? NPASS - 2 : 0) : 1][16],
+    fb_f2 *ring, unsigned tring, int rslot, int wslot, int R, int t, int T1, int L, fb_f2 alpha2,
+    const fb_f2 *pn, const fb_f2 *po, unsigned sk8, int next_rslot)
 {
     static_assert(U == 8, "one x16 tensor-memory access per ring and chunk");
     constexpr int NT = NPASS > 2 ? NPASS - 2 : 0;       // rings in tensor memory
     fb_f2 old0[U];
-    unsigned oldr[NT > 0 ? NT : 1][16];
     if (NPASS > 1) {
         if (rslot + U <= R) {
             const fb_f2 *a = ring + rslot * 32;
 #pragma unroll
             for (int j = 0; j < U; ++j) old0[j] = a[j * 32];
-            if (NT > 0) {
-#pragma unroll
-                for (int q = 0; q < NT; ++q) fb_tmem_ld16(tring + 2u * (unsigned)(q * R + rslot), oldr[q]);
-            }
         } else {
 #pragma unroll
             for (int j = 0; j < U; ++j) {
                 int rj = rslot + j;
                 rj = (rj >= R) ? rj - R : rj;
                 old0[j] = ring[rj * 32];
-#pragma unroll
-                for (int q = 0; q < NT; ++q) fb_tmem_ld2(tring + 2u * (unsigned)(q * R + rj), oldr[q][2 * j], oldr[q][2 * j + 1]);
             }
         }
         if (NT > 0) {
@@ -162,6 +189,10 @@ __device__ __forceinline__ void fb_sweep32_chunk(
                 const int k = t + j - (q + 1) * T1;
                 r = (k >= 0 && k < L) ? r : 0ull;
             }
+            if (PIPE && q == 0) {
+                bn[j] = fb_ldg2_here(fb_row(pn, (unsigned)j, sk8));
+                bo[j] = fb_ldg2_here(fb_row(po, (unsigned)j, sk8));
+            }
             x = r;
         }
         xs[j] = x;
@@ -170,6 +201,7 @@ __device__ __forceinline__ void fb_sweep32_chunk(
 #pragma unroll
         for (int q = 0; q < NT; ++q) fb_tmem_st16(tring + 2u * (unsigned)(q * R + wslot), newr[q]);
         fb_tmem_wait_st();
+        if (PIPE) fb_sweep32_tmem_issue<NT, U>(oldr, tring, next_rslot, R);
     }
 }
 
@@ -354,6 +386,7 @@ fb_sweep32_kernel(const FbSweep32 p)
     };
 
     fb_f2 xs[U];
+    unsigned oldr[NT > 0 ? NT : 1][16];
     int t = t_begin;
 #pragma unroll 1
     for (int phase = 0; phase < 2; ++phase) {
@@ -365,7 +398,9 @@ fb_sweep32_kernel(const FbSweep32 p)
                 prefetch_l2(t + FB32_L2_PREFETCH_CHUNKS * U, U);
                 load_ranged(bn, t);
                 load_ranged(bo, t - D);
-                fb_sweep32_chunk<NPASS, U, true>(bn, bo, accu, comp, new0, xs, ring, tring, rslot, wslot, R, t, T1, L, alpha2);
+                fb_sweep32_tmem_issue<NT, U>(oldr, tring, rslot, R);
+                fb_sweep32_chunk<NPASS, U, true, false>(bn, bo, accu, comp, new0, xs, oldr, ring, tring, rslot, wslot, R, t, T1, L, alpha2,
+                                                       nullptr, nullptr, 0u, 0);
                 const int kb = t - lag;
 #pragma unroll
                 for (int j = 0; j < U; ++j) {
@@ -382,34 +417,30 @@ fb_sweep32_kernel(const FbSweep32 p)
                 advance();
             }
         }
-        // interior: two register buffers alternate (the loads of chunk t+U fly while chunk t is computed)
+        // interior: software pipeline inside fb_sweep32_chunk (inputs and tensor-memory reads of chunk t+U are
+        // requested while chunk t is computed)
         if (phase == 0 && t < t_hi) {
-            fb_f2 an[U], ao[U], cn[U], co[U];
+            fb_f2 an[U], ao[U];
             load_inside(an, t);
             load_inside(ao, t - D);
+            fb_sweep32_tmem_issue<NT, U>(oldr, tring, rslot, R);
 #pragma unroll 1
-            for (;;) {
-                prefetch_l2(t + FB32_L2_PREFETCH_CHUNKS * U, 2 * U);          // the rows of this and the next chunk
-                {   // the chunk after the last interior one is loaded by the masked code: reload this one instead
-                    const int tn = (t + U < t_hi) ? t + U : t;
-                    load_inside(cn, tn);
-                    load_inside(co, tn - D);
-                }
-                fb_sweep32_chunk<NPASS, U, false>(an, ao, accu, comp, new0, xs, ring, tring, rslot, wslot, R, t, T1, L, alpha2);
+            for (; t < t_hi; t += U) {
+                prefetch_l2(t + FB32_L2_PREFETCH_CHUNKS * U, U);
+                // the chunk after the last interior one is loaded by the masked code: reload this one instead
+                const int tn = (t + U < t_hi) ? t + U : t;
+                const fb_f2 *pn = fb_row(in_safe, (unsigned)tn, sk8);
+                const fb_f2 *po = fb_row(in_safe, (unsigned)(tn - D), sk8);
+                int nr = rslot + U;
+                nr = (nr >= R) ? nr - R : nr;
+                fb_sweep32_chunk<NPASS, U, false, true>(an, ao, accu, comp, new0, xs, oldr, ring, tring, rslot, wslot, R, t, T1, L,
+                                                       alpha2, pn, po, sk8, nr);
                 emit_chunk(xs, t - lag);
                 advance();
-                t += U;
-                if (t >= t_hi) break;
-                {
-                    const int tn = (t + U < t_hi) ? t + U : t;
-                    load_inside(an, tn);
-                    load_inside(ao, tn - D);
-                }
-                fb_sweep32_chunk<NPASS, U, false>(cn, co, accu, comp, new0, xs, ring, tring, rslot, wslot, R, t, T1, L, alpha2);
-                emit_chunk(xs, t - lag);
-                advance();
-                t += U;
-                if (t >= t_hi) break;
+            }
+            if (NT > 0) {
+#pragma unroll
+                for (int q = 0; q < NT; ++q) fb_tmem_wait_ld16(oldr[q]);     // drain the reads issued by the last chunk
             }
         }
     }

@@ -656,3 +656,82 @@ def test_exact_methods_agree_with_convolution(fb):
     assert np.median(np.abs(radius[m] - naive[m])) < 0.01         # min_weight = 0.001 truncation
     rmse = np.sqrt(np.mean((conv[m] - naive[m]) ** 2))
     assert rmse < 0.5 and rmse < 0.05 * np.std(val)
+
+
+# ---------------------------------------------------------------------------------------------
+# fp32 working precision (north_star's fp32 path): tolerance-level parity, stated here
+
+def fp32_close(a, b, val_spread):
+    """
+    Tolerance of the fp32 path against the fp64 path (which is bit-identical to the reference):
+      * NaN masks differ on at most 1e-5 of the points (points whose weight is within fp32 rounding of the
+        max_dist threshold),
+      * RMS difference <= 1e-5 * spread of the values (a few float32 ulps of a field of magnitude 1000),
+      * max difference <= 1e-3 * spread (reached only next to the max_dist boundary, where the weights are 3e-4
+        of those inside clusters of samples).
+    """
+    assert a.shape == b.shape and a.dtype == b.dtype == np.float32
+    mism = np.isnan(a) != np.isnan(b)
+    assert mism.mean() <= 1e-5, mism.sum()
+    m = ~np.isnan(a) & ~np.isnan(b)
+    d = np.abs(a[m].astype(np.float64) - b[m].astype(np.float64))
+    assert np.sqrt(np.mean(d ** 2)) <= 1e-5 * val_spread, np.sqrt(np.mean(d ** 2))
+    assert d.max() <= 1e-3 * val_spread, d.max()
+    return True
+
+
+def test_fp32_path_paper_case(fb):
+    g = load_golden('c1_paper')
+    step = 1.0 / 32
+    x0 = np.asarray([-26.0 + step, 34.5])
+    size = (2400, 1200)
+    spread = float(g['val'].max() - g['val'].min())
+    naive = None
+    for method in ('optimized_convolution', 'convolution'):
+        for n in (2, 4, 6):
+            a = fb.barnes(g['pts'], g['val'], 1.0, x0, step, size, method=method, num_iter=n, precision='fp32')
+            b = fb.barnes(g['pts'], g['val'], 1.0, x0, step, size, method=method, num_iter=n)
+            assert fp32_close(a, b, spread)
+    # "matching RMSE against the naive method": the fp32 field is as close to the exact Gaussian sum as the fp64 one
+    naive = fb.barnes(g['pts'], g['val'], 1.0, x0, 0.25, (300, 150), method='naive')
+    a = fb.barnes(g['pts'], g['val'], 1.0, x0, 0.25, (300, 150), num_iter=4, precision='fp32')        # T = 3
+    b = fb.barnes(g['pts'], g['val'], 1.0, x0, 0.25, (300, 150), num_iter=4)
+    m = ~np.isnan(a) & ~np.isnan(b)
+    rmse32 = np.sqrt(np.mean((a[m] - naive[m]) ** 2))
+    rmse64 = np.sqrt(np.mean((b[m] - naive[m]) ** 2))
+    assert abs(rmse32 - rmse64) <= 1e-3 * rmse64
+
+
+def test_fp32_path_shapes_batches_3d(fb):
+    rng = np.random.default_rng(77)
+    pts = rng.uniform(0, 1, (20000, 2)) * [70, 35]
+    val = rng.normal(1000, 10, 20000)
+    spread = float(val.max() - val.min())
+    for size, sigma, step in (((1000, 517), 1.0, 1 / 16), ((333, 1201), 0.6, 1 / 16), ((70, 33), 1.5, 0.25), ((2001, 97), 0.8, 1 / 16)):
+        a = fb.barnes(pts, val, sigma, [0.0, 0.0], step, size, precision='fp32')
+        b = fb.barnes(pts, val, sigma, [0.0, 0.0], step, size)
+        assert fp32_close(a, b, spread)
+    # anisotropic sigma / step
+    a = fb.barnes(pts, val, [1.2, 0.7], [0.0, 0.0], [0.125, 0.0625], (500, 500), num_iter=3, precision='fp32')
+    b = fb.barnes(pts, val, [1.2, 0.7], [0.0, 0.0], [0.125, 0.0625], (500, 500), num_iter=3)
+    assert fp32_close(a, b, spread)
+    # batched == singles, bit for bit, also in fp32
+    B, N = 5, 3000
+    bp = rng.uniform(0, 1, (B, N, 2)) * [30, 20]
+    bv = rng.normal(0, 1, (B, N))
+    out = fb.barnes_batched(bp, bv, 1.0, [0.0, 0.0], 0.125, (241, 161), precision='fp32')
+    for i in range(B):
+        assert bits_equal(out[i], fb.barnes(bp[i], bv[i], 1.0, [0.0, 0.0], 0.125, (241, 161), precision='fp32'))
+    # 3D
+    p3 = rng.uniform(0, 1, (50000, 3)) * [60, 50, 40]
+    v3 = rng.normal(0, 1, 50000)
+    a = fb.barnes(p3, v3, 3.0, [0.0, 0.0, 0.0], 0.5, (121, 101, 81), precision='fp32')
+    b = fb.barnes(p3, v3, 3.0, [0.0, 0.0, 0.0], 0.5, (121, 101, 81))
+    assert fp32_close(a, b, float(v3.max() - v3.min()))
+    # what the fp32 path does not cover is refused, not approximated
+    with pytest.raises(RuntimeError, match='2D and 3D'):
+        fb.barnes(rng.uniform(0, 10, 100), rng.normal(0, 1, 100), 1.0, 0.0, 0.1, 101, precision='fp32')
+    with pytest.raises(RuntimeError, match='fp32 path does not cover'):
+        fb.barnes(pts, val, 0.1, [0.0, 0.0], 1 / 16, (200, 200), precision='fp32')       # T = 1
+    with pytest.raises(RuntimeError, match="'fp64' or 'fp32'"):
+        fb.barnes(pts, val, 1.0, [0.0, 0.0], 1 / 16, (200, 200), precision='fp16')
