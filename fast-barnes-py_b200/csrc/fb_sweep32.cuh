@@ -57,15 +57,6 @@ __device__ __forceinline__ fb_f2 fb2_fma(fb_f2 a, fb_f2 b, fb_f2 c)
     return r;
 }
 
-// base + j * stride_bytes as ONE instruction (IMAD.WIDE.U32) instead of a 64-bit shift-add chain
-template <typename T>
-__device__ __forceinline__ T *fb_row(T *base, unsigned j, unsigned stride_bytes)
-{
-    unsigned long long r;
-    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r) : "r"(j), "r"(stride_bytes), "l"((unsigned long long)base));
-    return reinterpret_cast<T *>(r);
-}
-
 // the address arithmetic above hides the address space from the compiler: state it in the access
 __device__ __forceinline__ fb_f2 fb_ldg2(const fb_f2 *q)
 {
