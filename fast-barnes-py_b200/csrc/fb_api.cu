@@ -643,7 +643,7 @@ int run_sweep(int mode, int num_iter, AxisParams ax, Pair &cur, Pair &spare, flo
             p.out_w = spare.w;
         }
         int rc = FB_OK;
-        if (g_tmem.load() == 3 && sweeph_fits(np, p.D) && p.n_outer * p.n_groups >= 8LL * sm_count_current() {
+        if (g_tmem.load() == 3 && sweeph_fits(np, p.D) && p.n_outer * p.n_groups >= 8LL * sm_count_current()) {
             // hybrid: two-warp pipelines, private rings in tensor memory, 8 pipelines per SM
             rc = launch_sweeph(m, np, p, st);
             if (rc != FB_OK) return rc;
