@@ -1584,6 +1584,7 @@ int slab_check(const fb_problem *pr, Derived &d, long long z_begin, long long z_
     int rc = derive(pr, d);
     if (rc != FB_OK) return rc;
     if (pr->dim != 3 || pr->nfields != 1) return fail(FB_EINVAL, "z-slab runs need dim == 3 and nfields == 1");
+    if (pr->flags & FB_FLAG_FP32) return fail(FB_EINVAL, "z-slab runs are fp64 only");
     if (z_begin < 0 || z_count < 1 || z_begin + z_count > d.Dz || halo_lo < 0 || halo_hi < 0 ||
         z_begin - halo_lo < 0 || z_begin + z_count + halo_hi > d.Dz)
         return fail(FB_EINVAL, "invalid slab: planes [%lld, %lld) halo %lld / %lld of %lld", z_begin, z_begin + z_count,
