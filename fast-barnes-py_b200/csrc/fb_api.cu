@@ -27,9 +27,7 @@ namespace {
 thread_local std::string g_err;
 std::atomic<long long> g_launches{0};
 std::atomic<int> g_profiling{0};
-thread_local bool t_skip_counter_zero = false;   // co-run: the work counter is shared and already zeroed
-// tensor-memory use of the sweeps: 0 none, 1 the all-TMEM one-warp kernel, 2 that kernel next to the
-// shared-memory kernels, 3 (default) the hybrid kernel for launches with enough work items
+// tensor-memory use of the fp64 sweeps: 0 none, non-zero (default) the hybrid kernel for launches with enough work items
 std::atomic<int> g_tmem{3};
 std::atomic<int> g_three_warp{1};   // tuning switch: three-stage sweep kernels on/off
 std::atomic<int> g_two_warp{1};     // tuning switch (fb_set_option): two-warp sweep kernels on/off
@@ -199,7 +197,7 @@ int launch_sweep2_t(const FbSweep &p, size_t smem, cudaStream_t st)
     }
     long long grid = (long long)occ[dev & 15] * sm_count(dev);
     if (grid > nitems) grid = nitems;
-    if (!t_skip_counter_zero) CUDA_TRY(cudaMemsetAsync(p.work_counter, 0, sizeof(unsigned long long), st));
+    CUDA_TRY(cudaMemsetAsync(p.work_counter, 0, sizeof(unsigned long long), st));
     fb_sweep2_kernel<NA, NB, MODE, FB_SWEEP_U><<<(unsigned)grid, 64, smem, st>>>(p);
     LAUNCH_CHECK();
     return FB_OK;
@@ -288,7 +286,7 @@ int launch_sweep3_t(const FbSweep &p, size_t smem, cudaStream_t st)
     }
     long long grid = (long long)occ[dev & 15] * sm_count(dev);
     if (grid > nitems) grid = nitems;
-    if (!t_skip_counter_zero) CUDA_TRY(cudaMemsetAsync(p.work_counter, 0, sizeof(unsigned long long), st));
+    CUDA_TRY(cudaMemsetAsync(p.work_counter, 0, sizeof(unsigned long long), st));
     fb_sweep3_kernel<S0, S1, S2, MODE, FB_SWEEP_U><<<(unsigned)grid, 96, smem, st>>>(p);
     LAUNCH_CHECK();
     return FB_OK;
@@ -481,49 +479,6 @@ int run_sweep32(int mode, int num_iter, const AxisParams &ax, const fb_f2 *src2,
     return launch_sweep32_m<2>(num_iter, p, st);
 }
 
-// tensor-memory kernel: 4 warps per CTA, one CTA per SM (it allocates all 512 TMEM columns)
-inline bool sweep_tmem_fits(int npass, int D)
-{
-    return sweep_chunk(D) == FB_SWEEP_U && (npass - 1) * sweep_ring_depth(D) * 2 <= 512;
-}
-
-template <int NPASS, int MODE>
-int launch_sweep_tmem_t(const FbSweep &p, cudaStream_t st, bool zero_counter)
-{
-    int dev = 0;
-    cudaGetDevice(&dev);
-    const long long nitems = p.n_outer * p.n_groups;
-    if (nitems <= 0) return FB_OK;
-    const size_t smem = MODE == 1 ? (size_t)4 * FB_TILE_K * FB_TILE_PITCH * sizeof(double) : 0;
-    long long grid = sm_count(dev);
-    if (grid > (nitems + 3) / 4) grid = (nitems + 3) / 4;
-    if (zero_counter) CUDA_TRY(cudaMemsetAsync(p.work_counter, 0, sizeof(unsigned long long), st));
-    fb_sweep_t_kernel<NPASS, MODE, FB_SWEEP_U><<<(unsigned)grid, 128, smem, st>>>(p);
-    LAUNCH_CHECK();
-    return FB_OK;
-}
-
-template <int MODE>
-int launch_sweep_tmem_m(int npass, const FbSweep &p, cudaStream_t st, bool zero_counter)
-{
-    switch (npass) {
-    case 1: return launch_sweep_tmem_t<1, MODE>(p, st, zero_counter);
-    case 2: return launch_sweep_tmem_t<2, MODE>(p, st, zero_counter);
-    case 3: return launch_sweep_tmem_t<3, MODE>(p, st, zero_counter);
-    case 4: return launch_sweep_tmem_t<4, MODE>(p, st, zero_counter);
-    case 5: return launch_sweep_tmem_t<5, MODE>(p, st, zero_counter);
-    case 6: return launch_sweep_tmem_t<6, MODE>(p, st, zero_counter);
-    }
-    return fail(FB_EINVAL, "unsupported number of fused passes: %d", npass);
-}
-
-int launch_sweep_tmem(int m, int npass, const FbSweep &p, cudaStream_t st, bool zero_counter)
-{
-    if (m == 0) return launch_sweep_tmem_m<0>(npass, p, st, zero_counter);
-    if (m == 1) return launch_sweep_tmem_m<1>(npass, p, st, zero_counter);
-    return launch_sweep_tmem_m<2>(npass, p, st, zero_counter);
-}
-
 template <int NPASS, int MODE, int U>
 int launch_sweep_t(const FbSweep &p, size_t smem, cudaStream_t st)
 {
@@ -549,7 +504,7 @@ int launch_sweep_t(const FbSweep &p, size_t smem, cudaStream_t st)
     }
     long long grid = (long long)occ[dev & 15] * sm_count(dev);
     if (grid > nitems) grid = nitems;
-    if (!t_skip_counter_zero) CUDA_TRY(cudaMemsetAsync(p.work_counter, 0, sizeof(unsigned long long), st));
+    CUDA_TRY(cudaMemsetAsync(p.work_counter, 0, sizeof(unsigned long long), st));
     fb_sweep_kernel<NPASS, MODE, U><<<(unsigned)grid, 32, smem, st>>>(p);
     LAUNCH_CHECK();
     return FB_OK;
@@ -574,17 +529,6 @@ int launch_sweep_m(int npass, const FbSweep &p, size_t smem, cudaStream_t st)
 {
     if (sweep_chunk(p.D) == FB_SWEEP_U) return launch_sweep_u<MODE, FB_SWEEP_U>(npass, p, smem, st);
     return launch_sweep_u<MODE, FB_SWEEP_U_SMALL>(npass, p, smem, st);
-}
-
-// side stream for the tensor-memory kernel when it runs next to a shared-memory kernel
-int side_stream_get(cudaStream_t *out)
-{
-    static cudaStream_t side[16] = {nullptr};
-    int dev = 0;
-    CUDA_TRY(cudaGetDevice(&dev));
-    if (!side[dev & 15]) CUDA_TRY(cudaStreamCreateWithFlags(&side[dev & 15], cudaStreamNonBlocking));
-    *out = side[dev & 15];
-    return FB_OK;
 }
 
 // A pair of fp64 grids (value field, weight field) in device memory.
@@ -643,35 +587,12 @@ int run_sweep(int mode, int num_iter, AxisParams ax, Pair &cur, Pair &spare, flo
             p.out_w = spare.w;
         }
         int rc = FB_OK;
-        if (g_tmem.load() == 3 && sweeph_fits(np, p.D) && p.n_outer * p.n_groups >= 8LL * sm_count_current()) {
+        if (g_tmem.load() != 0 && sweeph_fits(np, p.D) && p.n_outer * p.n_groups >= 8LL * sm_count_current()) {
             // hybrid: two-warp pipelines, private rings in tensor memory, 8 pipelines per SM
             rc = launch_sweeph(m, np, p, st);
             if (rc != FB_OK) return rc;
             if (m != 2 && !in_place) { Pair t2 = cur; cur = spare; spare = t2; }
             continue;
-        }
-        if (g_tmem.load() == 1 && sweep_tmem_fits(np, p.D)) {
-            // experimental: rings in tensor memory, this kernel alone
-            rc = launch_sweep_tmem(m, np, p, st, true);
-            if (rc != FB_OK) return rc;
-            if (m != 2 && !in_place) { Pair t2 = cur; cur = spare; spare = t2; }
-            continue;
-        }
-        // co-run: the tensor-memory kernel (no shared memory for rings) on a side stream next to the
-        // shared-memory kernel on the main stream; both claim work items from the same counter
-        const bool corun = g_tmem.load() == 2 && sweep_tmem_fits(np, p.D) && p.n_outer * p.n_groups >= 1024;
-        cudaStream_t side = nullptr;
-        cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-        if (corun) {
-            if ((rc = side_stream_get(&side)) != FB_OK) return rc;
-            CUDA_TRY(cudaMemsetAsync(p.work_counter, 0, sizeof(unsigned long long), st));
-            CUDA_TRY(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
-            CUDA_TRY(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
-            CUDA_TRY(cudaEventRecord(ev_fork, st));
-            CUDA_TRY(cudaStreamWaitEvent(side, ev_fork, 0));
-            if ((rc = launch_sweep_tmem(m, np, p, side, false)) != FB_OK) return rc;
-            CUDA_TRY(cudaEventRecord(ev_join, side));
-            t_skip_counter_zero = true;
         }
         // two warps per 16 lines when the launch fuses >= 2 passes (general chunk length only)
         const bool two_warps = g_two_warp.load() && (np >= 2 || m == 2) && sweep_chunk(p.D) == FB_SWEEP_U &&
@@ -699,15 +620,6 @@ int run_sweep(int mode, int num_iter, AxisParams ax, Pair &cur, Pair &spare, flo
             if (m == 0) rc = launch_sweep_m<0>(np, p, smem, st);
             else if (m == 1) rc = launch_sweep_m<1>(np, p, smem, st);
             else rc = launch_sweep_m<2>(np, p, smem, st);
-        }
-        if (corun) {
-            t_skip_counter_zero = false;
-            if (rc == FB_OK) {
-                cudaError_t e_ = cudaStreamWaitEvent(st, ev_join, 0);
-                if (e_ != cudaSuccess) rc = fail(FB_ECUDA, "cudaStreamWaitEvent failed: %s", cudaGetErrorString(e_));
-            }
-            cudaEventDestroy(ev_fork);
-            cudaEventDestroy(ev_join);
         }
         if (rc != FB_OK) return rc;
         if (m != 2 && !in_place) { Pair t = cur; cur = spare; spare = t; }

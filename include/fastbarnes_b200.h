@@ -209,9 +209,9 @@ int fb_barnes_s2_map_host(int64_t nsamples, const double *pts, const double *val
 /* process-wide tuning switches that never change results (bit-identical either way):
  *   "two_warp_sweeps" (default 1): sweep launches that fuse >= 2 passes use two warps per 16 lines
  *   "three_warp_sweeps" (default 1): 0 off, 1 three pipeline stages for the finalising sweep, 2 for all
- *   "tmem_sweeps" (default 3): tensor memory as ring storage: 0 off, 1 all rings in TMEM (one warp per 16
- *       lines), 2 that kernel beside the shared-memory kernels, 3 hybrid kernel (private rings in TMEM,
- *       hand-over ring in shared memory, 16 warps per SM) for launches with >= 8 work items per SM
+ *   "tmem_sweeps" (default 1): tensor memory as ring storage of the fp64 sweeps: 0 off, non-zero: hybrid
+ *       kernel (private rings in TMEM, hand-over ring in shared memory, 16 warps per SM) for launches
+ *       with >= 8 work items per SM
  *   "sweep2_na_shift" (default 0): moves passes between the two warps of the two-warp kernel
  *   "host_chunk_fields" (default 4): fields per chunk of the pipelined fb_barnes_host path      */
 int  fb_set_option(const char *name, int value);

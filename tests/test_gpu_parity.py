@@ -735,3 +735,66 @@ def test_fp32_path_shapes_batches_3d(fb):
         fb.barnes(pts, val, 0.1, [0.0, 0.0], 1 / 16, (200, 200), precision='fp32')       # T = 1
     with pytest.raises(RuntimeError, match="'fp64' or 'fp32'"):
         fb.barnes(pts, val, 1.0, [0.0, 0.0], 1 / 16, (200, 200), precision='fp16')
+
+
+# ---------------------------------------------------------------------------------------------
+# large batches: the hybrid sweep kernels (two-warp pipelines, rings in tensor memory) take over at >= 8 work
+# items per SM, i.e. only for batches like bench.py's; check them against the oracle and the shared-memory kernels
+
+@pytest.mark.parametrize('ratio,iters', [(8, (2, 3, 4, 5, 6)), (32, (4,))])
+def test_large_batch_hybrid_kernels(fb, orc, ratio, iters):
+    """ device-resident batches (the host entry point works in chunks of 4 fields and never gets there) """
+    torch = pytest.importorskip('torch')
+    from fastbarnes import _lib
+    L = _lib.lib()
+    rng = np.random.default_rng(1000 + ratio)
+    F, N = 40, 1500
+    size = (512, 500)                                   # 32 line groups per field and sweep: 1280 work items
+    step = 1.0 / ratio
+    ext = np.asarray([(size[0] - 1) * step, (size[1] - 1) * step])
+    pts = rng.uniform(0, 1, (F, N, 2)) * ext
+    pts[:, :100] = pts[:, 100:200]                      # repeated locations
+    val = rng.normal(1000, 10, (F, N))
+    d_pts = torch.from_numpy(pts.reshape(F * N, 2)).cuda()
+    d_val = torch.from_numpy(val.reshape(F * N)).cuda()
+
+    def run(method, n, precision='fp64'):
+        plan = fb.BarnesDevice(2, 1.0, [0.0, 0.0], step, size, nfields=F, nsamples=F * N, method=method, num_iter=n,
+                               precision=precision)
+        n0 = L.fb_kernel_launch_count()
+        out = plan(d_pts, d_val).cpu().numpy()
+        return out, L.fb_kernel_launch_count() - n0
+
+    for n in iters:
+        for method in (('optimized_convolution', 'convolution') if n == 4 else ('optimized_convolution',)):
+            out, _ = run(method, n)
+            try:
+                _lib.check(L.fb_set_option(b'tmem_sweeps', 0))
+                smem, _ = run(method, n)
+            finally:
+                L.fb_set_option(b'tmem_sweeps', 1)
+            assert bits_equal(out, smem), (n, method)
+            for i in (0, 17, F - 1):
+                ref = orc.barnes(pts[i], val[i], 1.0, [0.0, 0.0], step, size, method=method, num_iter=n, nthreads=4)
+                assert bits_equal(out[i], ref), (n, method, i)
+    # the fp32 path on the same batch
+    a, _ = run('optimized_convolution', 4, 'fp32')
+    b, _ = run('optimized_convolution', 4)
+    assert fp32_close(a, b, float(val.max() - val.min()))
+
+
+def test_3d_volume_hybrid_kernels(fb, orc):
+    """ a volume with >= 1184 line groups in every sweep: all three hybrid kernel modes (transposing x sweep,
+    in-place y sweep, finalising z sweep) against the oracle, bit for bit """
+    rng = np.random.default_rng(31)
+    size = (160, 128, 160)
+    step = 0.25
+    pts = rng.uniform(0, 1, (60000, 3)) * (np.asarray(size) - 1) * step
+    pts[:500] = pts[500:1000]
+    val = rng.normal(5.0, 2.0, 60000)
+    for n in (4, 5):
+        out = fb.barnes(pts, val, 1.0, [0.0, 0.0, 0.0], step, size, num_iter=n)
+        ref = orc.barnes(pts, val, 1.0, [0.0, 0.0, 0.0], step, size, num_iter=n, nthreads=8)
+        assert bits_equal(out, ref), n
+    a = fb.barnes(pts, val, 1.0, [0.0, 0.0, 0.0], step, size, num_iter=4, precision='fp32')
+    assert fp32_close(a, fb.barnes(pts, val, 1.0, [0.0, 0.0, 0.0], step, size, num_iter=4), float(val.max() - val.min()))
