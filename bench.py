@@ -377,7 +377,7 @@ def run_gpu(args, rank, local_rank, world):
                 'sweep_y_frac_of_peak': by * pts_launch / (s32[3] * 1e-3) / 1e9 / peak if s32[3] > 0 else 0.0}
         if world == 1 and not args.no_cpu:
             cores = os.cpu_count() or 1
-            nf = max(cores, 8) * 2
+            nf = max(cores, 8) * 6          # about 20 core-seconds of CPU work
             fps, secs = cpu_fields_per_second(nf, cores)
             line['cpu_baseline'] = {'value': fps * POINTS_PER_FIELD, 'unit': UNIT, 'cores': cores, 'kind': 'port',
                                     'sample': '%d fields of the same workload, one field per host thread, %.1f s wall'
