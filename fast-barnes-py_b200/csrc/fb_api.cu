@@ -29,6 +29,8 @@ std::atomic<long long> g_launches{0};
 std::atomic<int> g_profiling{0};
 // tensor-memory use of the fp64 sweeps: 0 none, non-zero (default) the hybrid kernel for launches with enough work items
 std::atomic<int> g_tmem{3};
+// fp64 injection as interleaved (value, weight) nodes when the hybrid x sweep consumes it: 0 off, non-zero (default) on
+std::atomic<int> g_interleaved{1};
 std::atomic<int> g_three_warp{1};   // tuning switch: three-stage sweep kernels on/off
 std::atomic<int> g_two_warp{1};     // tuning switch (fb_set_option): two-warp sweep kernels on/off
 
@@ -339,17 +341,17 @@ inline bool sweeph_fits(int npass, int D)
            2 * (sweeph_smem_bytes(1, D) + 1024) <= kSmemPerSM;      // at least two CTAs (four pipelines) per SM
 }
 
-template <int NA, int NB, int MODE>
-int launch_sweeph_t(FbSweep p, int npass, cudaStream_t st)
+template <int NA, int NB, int MODE, int ES>
+int launch_sweeph_es(FbSweep p, int npass, cudaStream_t st)
 {
     static thread_local size_t configured[16] = {0};
     int dev = 0;
     cudaGetDevice(&dev);
     const size_t smem = sweeph_smem_bytes(MODE, p.D);
     if (smem > 40 * 1024 && configured[dev & 15] < smem) {     // static shared memory counts too
-        CUDA_TRY(cudaFuncSetAttribute(fb_sweeph_kernel<NA, NB, MODE, FB_SWEEP_U>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        CUDA_TRY(cudaFuncSetAttribute(fb_sweeph_kernel<NA, NB, MODE, FB_SWEEP_U, ES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)kSmemLimit));
-        CUDA_TRY(cudaFuncSetAttribute(fb_sweeph_kernel<NA, NB, MODE, FB_SWEEP_U>, cudaFuncAttributePreferredSharedMemoryCarveout,
+        CUDA_TRY(cudaFuncSetAttribute(fb_sweeph_kernel<NA, NB, MODE, FB_SWEEP_U, ES>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                       cudaSharedmemCarveoutMaxShared));
         configured[dev & 15] = kSmemLimit;
     }
@@ -367,9 +369,19 @@ int launch_sweeph_t(FbSweep p, int npass, cudaStream_t st)
     if (grid > (nitems + 1) / 2) grid = (nitems + 1) / 2;
     if (getenv("FB_DEBUG")) fprintf(stderr, "[fb] sweeph<%d,%d,%d> smem %zu occ %d tmem_cols %d per_sm %d grid %lld items %lld\n", NA, NB, MODE, smem, occ_est, p.tmem_cols, per_sm, grid, nitems);
     CUDA_TRY(cudaMemsetAsync(p.work_counter, 0, sizeof(unsigned long long), st));
-    fb_sweeph_kernel<NA, NB, MODE, FB_SWEEP_U><<<(unsigned)grid, 128, smem, st>>>(p);
+    fb_sweeph_kernel<NA, NB, MODE, FB_SWEEP_U, ES><<<(unsigned)grid, 128, smem, st>>>(p);
     LAUNCH_CHECK();
     return FB_OK;
+}
+
+template <int NA, int NB, int MODE>
+int launch_sweeph_t(const FbSweep &p, int npass, cudaStream_t st)
+{
+    if constexpr (MODE == 1) {
+        if (p.in_es == 2) return launch_sweeph_es<NA, NB, 1, 2>(p, npass, st);
+    }
+    if (p.in_es != 1) return fail(FB_EINVAL, "internal: interleaved input is read by the transposing sweep only");
+    return launch_sweeph_es<NA, NB, MODE, 1>(p, npass, st);
 }
 
 template <int MODE>
@@ -541,9 +553,27 @@ struct Pair { double *v, *w; };
 // wide kernels degrade to one launch per pass).  Launches with f >= 2 that keep the layout run in
 // place; single-pass launches and the transposing launch write to `spare`, after which the roles
 // of the two pairs swap.  On return `cur` holds the result (modes 0 and 1).
+// largest number of passes one launch can fuse / launches of a sweep / does its (single) launch run the hybrid kernel
+inline int sweep_fmax(int mode, int D)
+{
+    int fmax = 1;
+    for (int f = 2; f <= FB_MAX_FUSED_PASSES; ++f)
+        if (sweep_smem_bytes(f, mode, D) <= kSmemLimit) fmax = f;
+    return fmax;
+}
+inline bool sweep_is_single_hybrid(int mode, int num_iter, int T, long long n_outer, long long n_inner)
+{
+    const int D = 2 * T + 2;
+    const int fmax = sweep_fmax(mode, D);
+    if ((num_iter + fmax - 1) / fmax != 1) return false;
+    return g_tmem.load() != 0 && sweeph_fits(num_iter, D) && n_outer * ((n_inner + 15) / 16) >= 8LL * sm_count_current();
+}
+
+// interleaved_in: `cur` is the injection grid in its interleaved form (cur.v = first value, cur.w = cur.v + 1);
+// only valid when sweep_is_single_hybrid() holds for this sweep.
 int run_sweep(int mode, int num_iter, AxisParams ax, Pair &cur, Pair &spare, float *out32, double *out64,
               const unsigned long long *mm, double csf, long long n_outer, long long L, long long n_inner,
-              bool has_w, cudaStream_t st, SweepCounters &ctr)
+              bool has_w, cudaStream_t st, SweepCounters &ctr, bool interleaved_in = false)
 {
     FbSweep p{};
     p.n_outer = n_outer;
@@ -561,11 +591,11 @@ int run_sweep(int mode, int num_iter, AxisParams ax, Pair &cur, Pair &spare, flo
     p.out64 = out64;
     if (L > 2147483647LL - 8 * (long long)(ax.T + 1) - 64) return fail(FB_EINVAL, "line too long: %lld", L);
 
-    // largest number of passes one launch can fuse
-    int fmax = 1;
-    for (int f = 2; f <= FB_MAX_FUSED_PASSES; ++f)
-        if (sweep_smem_bytes(f, mode, p.D) <= kSmemLimit) fmax = f;
+    p.in_es = 1;
+    const int fmax = sweep_fmax(mode, p.D);
     const int nlaunch = (num_iter + fmax - 1) / fmax;
+    if (interleaved_in && !(has_w && sweep_is_single_hybrid(mode, num_iter, ax.T, n_outer, n_inner)))
+        return fail(FB_EINVAL, "internal: interleaved input needs the single-launch hybrid sweep");
     int remaining = num_iter;
     for (int l = 0; l < nlaunch; ++l) {
         const int np = (remaining + (nlaunch - l) - 1) / (nlaunch - l);
@@ -589,6 +619,7 @@ int run_sweep(int mode, int num_iter, AxisParams ax, Pair &cur, Pair &spare, flo
         int rc = FB_OK;
         if (g_tmem.load() != 0 && sweeph_fits(np, p.D) && p.n_outer * p.n_groups >= 8LL * sm_count_current()) {
             // hybrid: two-warp pipelines, private rings in tensor memory, 8 pipelines per SM
+            p.in_es = interleaved_in ? 2 : 1;
             rc = launch_sweeph(m, np, p, st);
             if (rc != FB_OK) return rc;
             if (m != 2 && !in_place) { Pair t2 = cur; cur = spare; spare = t2; }
@@ -707,8 +738,8 @@ void carve(Workspace &w, char *base, const fb_problem *pr, long long total, long
     auto take = [&](size_t n) { char *p = base ? base + off : nullptr; off += align_up(n); return p; };
     const size_t g = (size_t)pr->nfields * (size_t)total * sizeof(double);
     const size_t R = (size_t)nsamples << pr->dim;
-    w.vA = (double *)take(g);
-    w.wA = (double *)take(g);
+    w.vA = (double *)take(2 * g);                           // one block: also holds the interleaved (value, weight) form
+    w.wA = base ? (double *)((char *)w.vA + g) : nullptr;
     w.vB = (double *)take(g);
     w.wB = (double *)take(g);
     w.mm = (unsigned long long *)take((size_t)pr->nfields * FB_MM_STRIDE * 8);
@@ -748,8 +779,9 @@ int check_offsets(const fb_problem *pr, long long nsamples, const int64_t *off, 
 // z_off / z_cnt: z window of the injected buffers (z-slab runs); the whole grid is (0, d.Dz).
 int run_inject(const fb_problem *pr, const Derived &d, long long nsamples, const int64_t *h_offsets,
                const double *d_pts, const double *d_val, Workspace &w, cudaStream_t st,
-               long long z_off = 0, long long z_cnt = -1, bool f32 = false)
+               long long z_off = 0, long long z_cnt = -1, bool f32 = false, bool il64 = false)
 {
+    // il64: the injected grid is ONE array of interleaved double2 (value, weight) nodes in w.vA (FORM 2)
     // f32: the injected grid is ONE array of interleaved float2 (value, weight) nodes in w.vA (fp32 path)
     if (z_cnt < 0) z_cnt = d.Dz;
     const long long slab_total = d.W * d.H * z_cnt;
@@ -803,6 +835,15 @@ int run_inject(const fb_problem *pr, const Derived &d, long long nsamples, const
         LAUNCH_CHECK();
         fb_inject_reduce_kernel<true><<<(unsigned)rblocks, 128, 0, st>>>(w.counters, w.seg_node, w.seg_base, w.seg_n,
                                                                                w.rec_k, w.rec_w, w.rec_wv, w.vA, w.wA);
+    } else if (il64) {
+        fb_inject_count_kernel<2><<<sg, 256, 0, st>>>(s, gr, w.vA, w.wA, w.first_mask);
+        LAUNCH_CHECK();
+        fb_inject_alloc_kernel<2><<<sg, 256, 0, st>>>(s, gr, w.vA, w.wA, w.first_mask, w.counters, w.seg_node, w.seg_base, w.seg_n);
+        LAUNCH_CHECK();
+        fb_inject_place_kernel<2><<<sg, 256, 0, st>>>(s, gr, w.vA, w.wA, w.mm, w.rec_k, w.rec_w, w.rec_wv);
+        LAUNCH_CHECK();
+        fb_inject_reduce_kernel<2><<<(unsigned)rblocks, 128, 0, st>>>(w.counters, w.seg_node, w.seg_base, w.seg_n,
+                                                                            w.rec_k, w.rec_w, w.rec_wv, w.vA, w.wA);
     } else {
         fb_inject_count_kernel<false><<<sg, 256, 0, st>>>(s, gr, w.vA, w.wA, w.first_mask);
         LAUNCH_CHECK();
@@ -815,6 +856,14 @@ int run_inject(const fb_problem *pr, const Derived &d, long long nsamples, const
     }
     LAUNCH_CHECK();
     return FB_OK;
+}
+
+// The fp64 injection writes interleaved (value, weight) nodes when the x sweep that consumes them is the
+// hybrid kernel in a single launch (2D / 3D whole-grid path only; the z-slab path keeps planes).
+bool inject_interleaved(const fb_problem *pr, const Derived &d)
+{
+    if (pr->dim < 2 || (pr->flags & FB_FLAG_FP32) || g_interleaved.load() == 0) return false;
+    return sweep_is_single_hybrid(1, pr->num_iter, d.ax[0].T, (long long)pr->nfields * d.Dz, d.H);
 }
 
 int run_sweeps(const fb_problem *pr, const Derived &d, Workspace &w, float *d_out, double *d_out64, cudaStream_t st,
@@ -866,7 +915,9 @@ int run_sweeps(const fb_problem *pr, const Derived &d, Workspace &w, float *d_ou
         return prof_mark(5, st);
     }
     // x sweep: A layout [..][x][y] -> natural layout [..][y][x]
-    rc = run_sweep(1, n, d.ax[0], cur, spare, nullptr, nullptr, w.mm, d.csf, nf * d.Dz, d.W, d.H, true, st, ctr);
+    if (inject_interleaved(pr, d)) cur = Pair{w.vA, w.vA + 1};       // interleaved (value, weight) nodes
+    rc = run_sweep(1, n, d.ax[0], cur, spare, nullptr, nullptr, w.mm, d.csf, nf * d.Dz, d.W, d.H, true, st, ctr,
+                   inject_interleaved(pr, d));
     if (rc != FB_OK) return rc;
     if ((rc = prof_mark(3, st)) != FB_OK) return rc;
     if (pr->dim == 2) {
@@ -914,7 +965,8 @@ int pipeline(const fb_problem *pr, long long nsamples, const int64_t *h_offsets,
     g_prof.launches_begin = g_launches.load();
     g_prof.marked = 0;
     if ((rc = prof_mark(0, st)) != FB_OK) return rc;
-    rc = run_inject(pr, d, nsamples, h_offsets, d_pts, d_val, w, st, 0, -1, (pr->flags & FB_FLAG_FP32) != 0);
+    rc = run_inject(pr, d, nsamples, h_offsets, d_pts, d_val, w, st, 0, -1, (pr->flags & FB_FLAG_FP32) != 0,
+                    inject_interleaved(pr, d));
     if (rc != FB_OK) return rc;
     if ((rc = prof_mark(2, st)) != FB_OK) return rc;
     rc = run_sweeps(pr, d, w, d_out, d_out64, st, sp);
@@ -1824,6 +1876,7 @@ FB_EXPORT int fb_set_option(const char *name, int value)
     if (!strcmp(name, "three_warp_sweeps")) { g_three_warp.store(value ? 1 : 0); return FB_OK; }
     if (!strcmp(name, "sweep2_na_shift")) { g_na_shift.store(value); return FB_OK; }
     if (!strcmp(name, "tmem_sweeps")) { g_tmem.store(value); return FB_OK; }
+    if (!strcmp(name, "interleaved_inject")) { g_interleaved.store(value); return FB_OK; }
     if (!strcmp(name, "host_chunk_fields")) { g_host_chunk_fields.store(value); return FB_OK; }
     return fail(FB_EINVAL, "unknown option: %s", name);
 }
