@@ -47,6 +47,8 @@ BYTES_SWEEP_Y = 20   # final fused sweep: 2 x 8 B read + 4 B float32 write
 BYTES_TOTAL_2D = 68
 
 
+_JSON_OUT = None   # set by main(): duplicate of the original stdout
+
 def make_fields(first_field, nfields):
     """ synthetic samples of fields [first_field, first_field+nfields): SURVEY.md section 8d, config C5 """
     pts = np.empty((nfields, N_PER_FIELD, 2))
@@ -122,7 +124,7 @@ def run_reference(args, rank, world):
             'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
             'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_JSON_OUT or sys.stdout, flush=True)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -382,7 +384,7 @@ def run_gpu(args, rank, local_rank, world):
             line['cpu_baseline'] = {'value': fps * POINTS_PER_FIELD, 'unit': UNIT, 'cores': cores, 'kind': 'port',
                                     'sample': '%d fields of the same workload, one field per host thread, %.1f s wall'
                                               % (nf, secs)}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_JSON_OUT or sys.stdout, flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -399,6 +401,13 @@ def main():
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--no-fp32', action='store_true', help='skip the secondary fp32 working-precision measurement')
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line.  Libraries write there too (NCCL prints its version banner with
+    # printf), so file descriptor 1 is pointed at stderr and the JSON line goes to a duplicate of the
+    # original stdout.
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), 'w')
+    os.dup2(2, 1)
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -411,7 +420,7 @@ def main():
                '--master-addr', '127.0.0.1', '--master-port', str(29500 + os.getpid() % 1000), os.path.abspath(__file__),
                '--gpus', str(args.gpus), '--steps', str(args.steps), '--warmup', str(args.warmup),
                '--fields', str(args.fields), '--streams', str(args.streams)]
-        sys.exit(subprocess.call(cmd))
+        sys.exit(subprocess.call(cmd, stdout=_JSON_OUT))     # the ranks' stdout is the original stdout
     run_gpu(args, rank, local_rank, world)
 
 
