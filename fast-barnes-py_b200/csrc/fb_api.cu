@@ -31,6 +31,8 @@ std::atomic<int> g_profiling{0};
 std::atomic<int> g_tmem{3};
 // fp64 injection as interleaved (value, weight) nodes when the hybrid x sweep consumes it: 0 off, non-zero (default) on
 std::atomic<int> g_interleaved{1};
+// interleaved form: records linked into per-node lists (two passes over the samples) instead of count / allocate / place
+std::atomic<int> g_inject_lists{1};
 std::atomic<int> g_three_warp{1};   // tuning switch: three-stage sweep kernels on/off
 std::atomic<int> g_two_warp{1};     // tuning switch (fb_set_option): two-warp sweep kernels on/off
 
@@ -728,6 +730,7 @@ struct Workspace {
     long long *seg_node;
     unsigned int *seg_base, *seg_n;
     double *seg[4];          // 1D segmented path: extended segments (v, w) x (in, out)
+    unsigned int *link_next; // two-pass injection: successor of every record in its node's list
     size_t bytes;
 };
 
@@ -754,6 +757,7 @@ void carve(Workspace &w, char *base, const fb_problem *pr, long long total, long
     w.seg_n = (unsigned int *)take(R * 4 + 4);
     for (int i = 0; i < 4; ++i)
         w.seg[i] = (sp && sp->on) ? (double *)take((size_t)sp->Le * sp->n_seg * sizeof(double)) : nullptr;
+    w.link_next = (unsigned int *)take(R * 4 + 4);
     w.bytes = off;
 }
 
@@ -835,6 +839,15 @@ int run_inject(const fb_problem *pr, const Derived &d, long long nsamples, const
         LAUNCH_CHECK();
         fb_inject_reduce_kernel<true><<<(unsigned)rblocks, 128, 0, st>>>(w.counters, w.seg_node, w.seg_base, w.seg_n,
                                                                                w.rec_k, w.rec_w, w.rec_wv, w.vA, w.wA);
+    } else if (il64 && g_inject_lists.load() != 0) {
+        // two passes over the samples: link the records of every node into a list, then finish the lists
+        fb_inject_link_kernel<2><<<sg, 256, 0, st>>>(s, gr, w.vA, w.wA, w.link_next);
+        LAUNCH_CHECK();
+        fb_inject_finish_kernel<2><<<sg, 256, 0, st>>>(s, gr, w.vA, w.wA, w.link_next, w.mm, w.counters, w.seg_node, w.seg_base,
+                                                      w.seg_n, w.rec_k, w.rec_w, w.rec_wv);
+        LAUNCH_CHECK();
+        fb_inject_reduce_kernel<2><<<(unsigned)rblocks, 128, 0, st>>>(w.counters, w.seg_node, w.seg_base, w.seg_n,
+                                                                            w.rec_k, w.rec_w, w.rec_wv, w.vA, w.wA);
     } else if (il64) {
         fb_inject_count_kernel<2><<<sg, 256, 0, st>>>(s, gr, w.vA, w.wA, w.first_mask);
         LAUNCH_CHECK();
@@ -1877,6 +1890,7 @@ FB_EXPORT int fb_set_option(const char *name, int value)
     if (!strcmp(name, "sweep2_na_shift")) { g_na_shift.store(value); return FB_OK; }
     if (!strcmp(name, "tmem_sweeps")) { g_tmem.store(value); return FB_OK; }
     if (!strcmp(name, "interleaved_inject")) { g_interleaved.store(value); return FB_OK; }
+    if (!strcmp(name, "inject_lists")) { g_inject_lists.store(value); return FB_OK; }
     if (!strcmp(name, "host_chunk_fields")) { g_host_chunk_fields.store(value); return FB_OK; }
     return fail(FB_EINVAL, "unknown option: %s", name);
 }

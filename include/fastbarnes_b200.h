@@ -212,6 +212,10 @@ int fb_barnes_s2_map_host(int64_t nsamples, const double *pts, const double *val
  *   "tmem_sweeps" (default 1): tensor memory as ring storage of the fp64 sweeps: 0 off, non-zero: hybrid
  *       kernel (private rings in TMEM, hand-over ring in shared memory, 16 warps per SM) for launches
  *       with >= 8 work items per SM
+ *   "interleaved_inject" (default 1): the fp64 injection writes interleaved (value, weight) nodes whenever the
+ *       hybrid kernel runs the x sweep in one launch (one DRAM sector per record instead of two)
+ *   "inject_lists" (default 1): with interleaved nodes, link the records of a node into a list (two passes over
+ *       the samples) instead of count / allocate / place (three)
  *   "sweep2_na_shift" (default 0): moves passes between the two warps of the two-warp kernel
  *   "host_chunk_fields" (default 4): fields per chunk of the pipelined fb_barnes_host path      */
 int  fb_set_option(const char *name, int value);

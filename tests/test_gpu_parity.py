@@ -783,6 +783,46 @@ def test_large_batch_hybrid_kernels(fb, orc, ratio, iters):
     assert fp32_close(a, b, float(val.max() - val.min()))
 
 
+def test_injection_lists_vs_segments(fb, orc):
+    """ Interleaved fp64 nodes (the form the hybrid x sweep reads): the two-pass injection that links the
+    records of a node into a list against the three-pass count / allocate / place version and the oracle,
+    bit for bit -- random samples, repeated locations (lists of 25 records: heap sort; of 2: insertion sort)
+    and fields with every sample in a single cell or at a single location (lists of 1500 records). """
+    torch = pytest.importorskip('torch')
+    from fastbarnes import _lib
+    L = _lib.lib()
+    rng = np.random.default_rng(77)
+    F, N = 40, 1500
+    size = (512, 500)
+    step = 0.125
+    ext = np.asarray([(size[0] - 1) * step, (size[1] - 1) * step])
+    pts = rng.uniform(0, 1, (F, N, 2)) * ext
+    pts[0, :100] = pts[0, 100:200]                          # pairs
+    pts[1, :600] = pts[1, 600:625].repeat(24, axis=0)       # 25 records on each node of 25 cells
+    pts[2] = (np.asarray([200.25, 300.75]) + rng.uniform(0, 0.5, (N, 2))) * step   # one cell
+    pts[3, :] = pts[3, 0]                                   # one location
+    val = rng.normal(1000, 10, (F, N))
+    d_pts = torch.from_numpy(pts.reshape(F * N, 2)).cuda()
+    d_val = torch.from_numpy(val.reshape(F * N)).cuda()
+    plan = fb.BarnesDevice(2, 1.0, [0.0, 0.0], step, size, nfields=F, nsamples=F * N, num_iter=4, want_float64=True)
+    out = plan(d_pts, d_val).cpu().numpy()
+    out64 = plan.out64.cpu().numpy()
+    try:
+        _lib.check(L.fb_set_option(b'inject_lists', 0))
+        seg = plan(d_pts, d_val).cpu().numpy()
+        seg64 = plan.out64.cpu().numpy()
+        _lib.check(L.fb_set_option(b'interleaved_inject', 0))
+        planes = plan(d_pts, d_val).cpu().numpy()
+    finally:
+        L.fb_set_option(b'inject_lists', 1)
+        L.fb_set_option(b'interleaved_inject', 1)
+    assert bits_equal(out, seg) and bits_equal(out, planes)
+    assert np.array_equal(out64.view(np.uint64), seg64.view(np.uint64))
+    for i in (0, 1, 2, 3, F - 1):
+        ref = orc.barnes(pts[i], val[i], 1.0, [0.0, 0.0], step, size, num_iter=4, nthreads=4)
+        assert bits_equal(out[i], ref), i
+
+
 def test_3d_volume_hybrid_kernels(fb, orc):
     """ a volume with >= 1184 line groups in every sweep: all three hybrid kernel modes (transposing x sweep,
     in-place y sweep, finalising z sweep) against the oracle, bit for bit """
