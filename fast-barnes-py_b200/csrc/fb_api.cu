@@ -830,7 +830,15 @@ int run_inject(const fb_problem *pr, const Derived &d, long long nsamples, const
     const long long R = nsamples << pr->dim;
     long long rblocks = (R + 127) / 128;
     if (rblocks > 148 * 16) rblocks = 148 * 16;
-    if (f32) {
+    if (f32 && g_inject_lists.load() != 0) {
+        fb_inject_link_kernel<1><<<sg, 256, 0, st>>>(s, gr, w.vA, w.wA, w.link_next);
+        LAUNCH_CHECK();
+        fb_inject_finish_kernel<1><<<sg, 256, 0, st>>>(s, gr, w.vA, w.wA, w.link_next, w.mm, w.counters, w.seg_node, w.seg_base,
+                                                      w.seg_n, w.rec_k, w.rec_w, w.rec_wv);
+        LAUNCH_CHECK();
+        fb_inject_reduce_kernel<true><<<(unsigned)rblocks, 128, 0, st>>>(w.counters, w.seg_node, w.seg_base, w.seg_n,
+                                                                               w.rec_k, w.rec_w, w.rec_wv, w.vA, w.wA);
+    } else if (f32) {
         fb_inject_count_kernel<true><<<sg, 256, 0, st>>>(s, gr, w.vA, w.wA, w.first_mask);
         LAUNCH_CHECK();
         fb_inject_alloc_kernel<true><<<sg, 256, 0, st>>>(s, gr, w.vA, w.wA, w.first_mask, w.counters, w.seg_node, w.seg_base, w.seg_n);
