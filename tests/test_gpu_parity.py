@@ -821,6 +821,21 @@ def test_injection_lists_vs_segments(fb, orc):
     for i in (0, 1, 2, 3, F - 1):
         ref = orc.barnes(pts[i], val[i], 1.0, [0.0, 0.0], step, size, num_iter=4, nthreads=4)
         assert bits_equal(out[i], ref), i
+    # ragged fields (one empty, one with a single sample) and samples outside the grid
+    counts = rng.integers(800, 1500, F)
+    counts[4] = 0
+    counts[5] = 1
+    offs = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    rp = rng.uniform(-0.05, 1.05, (int(offs[-1]), 2)) * ext          # ~10 % of the samples are skipped
+    rv = rng.normal(5.0, 2.0, int(offs[-1]))
+    plan = fb.BarnesDevice(2, 1.0, [0.0, 0.0], step, size, nfields=F, nsamples=int(offs[-1]), num_iter=4,
+                           sample_offsets=offs)
+    out = plan(torch.from_numpy(rp).cuda(), torch.from_numpy(rv).cuda()).cpu().numpy()
+    assert np.isnan(out[4]).all()
+    for i in (0, 5, 6, F - 1):
+        a, b = int(offs[i]), int(offs[i + 1])
+        ref = orc.barnes(rp[a:b], rv[a:b], 1.0, [0.0, 0.0], step, size, num_iter=4, nthreads=4)
+        assert bits_equal(out[i], ref), i
 
 
 def test_3d_volume_hybrid_kernels(fb, orc):
