@@ -187,6 +187,31 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------------------------
 
+def bind_to_gpu_numa_node(torch, local_rank):
+    """ Multi-GPU runs: pin this rank to the CPUs next to its GPU (sysfs local_cpulist of the PCI device) before
+    it allocates pinned host buffers, so that those land in the GPU's NUMA node and the end-to-end arm's
+    host<->device copies of the ranks do not all cross the socket interconnect.  Returns the CPU list used. """
+    try:
+        pr = torch.cuda.get_device_properties(local_rank)
+        bus = '%04x:%02x:%02x.0' % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        with open('/sys/bus/pci/devices/%s/local_cpulist' % bus) as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(','):
+            if '-' in part:
+                a, b = part.split('-')
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return spec
+    except Exception as e:                       # no sysfs / no permission: run unbound
+        sys.stderr.write('[bench] NUMA binding skipped: %r\n' % (e,))
+    return None
+
+
 def run_gpu(args, rank, local_rank, world):
     import torch
     import torch.distributed as dist
@@ -196,6 +221,7 @@ def run_gpu(args, rank, local_rank, world):
     torch.cuda.set_device(local_rank)
     _lib.check(_lib.lib().fb_set_device(local_rank))
     dev = torch.device('cuda', local_rank)
+    numa = bind_to_gpu_numa_node(torch, local_rank) if world > 1 else None
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
     F = args.fields
@@ -345,7 +371,8 @@ def run_gpu(args, rank, local_rank, world):
             'dtype': 'f64', 'data': 'synthetic', 'config': config_dict(F, world),
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d * world, 'd2h_bytes_per_step': d2h * world,
                     'ms_per_step': e2e_ms / e2e_steps, 'steps': e2e_steps,
-                    'api': 'fb_barnes_host (C ABI, pinned host buffers, H2D + kernels + D2H inside)'},
+                    'api': 'fb_barnes_host (C ABI, pinned host buffers, H2D + kernels + D2H inside)',
+                    'host_cpus': numa},
             'gpu_launches': int(launches),
             'roofline': {
                 'bound': 'hbm',
