@@ -376,8 +376,8 @@ def run_gpu(args, rank, local_rank, world):
             'gpu_launches': int(launches),
             'roofline': {
                 'bound': 'hbm',
-                'kernel': 'fb_sweeph_kernel<2,2,1,8> (x sweep: 4 fused passes, two-warp pipelines, rings in tensor memory, transposing output)' if dominant_is_x
-                          else 'fb_sweeph_kernel<2,2,2,8> (y sweep: 4 fused passes + mask/divide/cast, two-warp pipelines, rings in tensor memory)',
+                'kernel': 'fb_sweeph_kernel<2,2,1,8,2> (x sweep: 4 fused passes, two-warp pipelines, rings in tensor memory, interleaved (value, weight) input, transposing output)' if dominant_is_x
+                          else 'fb_sweeph_kernel<2,2,2,8,1> (y sweep: 4 fused passes + mask/divide/cast, two-warp pipelines, rings in tensor memory)',
                 'achieved': gx if dominant_is_x else gy, 'peak': peak, 'unit': 'GB/s',
                 'frac': (gx if dominant_is_x else gy) / peak, 'traffic': traffic, 'peak_source': peak_src,
                 'algorithmic_bytes_per_point': BYTES_SWEEP_X if dominant_is_x else BYTES_SWEEP_Y,
