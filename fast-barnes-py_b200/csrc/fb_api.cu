@@ -9,6 +9,7 @@
 #include "fb_kernels.cuh"
 #include "fb_exact.cuh"
 #include "fb_sweep32.cuh"
+#include "fb_sweepq.cuh"
 
 #include <atomic>
 #include <cmath>
@@ -35,6 +36,11 @@ std::atomic<int> g_interleaved{1};
 std::atomic<int> g_inject_lists{1};
 std::atomic<int> g_three_warp{1};   // tuning switch: three-stage sweep kernels on/off
 std::atomic<int> g_two_warp{1};     // tuning switch (fb_set_option): two-warp sweep kernels on/off
+// second-generation sweep kernels (fb_sweepq.cuh): 0 off, non-zero (default) on for 2D / 3D fp64 grids they cover
+std::atomic<int> g_sweepq{1};
+std::atomic<int> g_q_nst{3};        // staging slots (chunks of rows in flight) per warp
+std::atomic<int> g_q_pf{0};         // extra chunks of lead of the L2 prefetch (0: none)
+std::atomic<int> g_q_warps{8};      // warps per CTA the plan starts with (8 or 4)
 
 int fail(int code, const char *fmt, ...)
 {
@@ -404,6 +410,189 @@ int launch_sweeph(int m, int npass, const FbSweep &p, cudaStream_t st)
     if (m == 0) return launch_sweeph_m<0>(npass, p, st);
     if (m == 1) return launch_sweeph_m<1>(npass, p, st);
     return launch_sweeph_m<2>(npass, p, st);
+}
+
+// ---- second-generation sweeps: fb_sweepq_kernel ------------------------------------------------------------------
+// Launch plan of one axis: warps per CTA (one CTA per SM), rings in shared memory (ns; the other
+// npass - 1 - ns rings sit in tensor memory), staging depth, per-warp shared-memory layout.
+struct SweepQPlan {
+    bool ok;
+    int warps, ns, nst, R, RP, cols_per_warp, smem_per_warp, off_ring;
+};
+constexpr size_t kQSmemLimit = 227 * 1024 - 1024;        // opt-in limit per CTA minus the kernel's static shared memory (1 KB with the alignment)
+
+// dynamic shared memory of a q-sweep CTA: output tiles + the warps' blocks
+inline size_t sweepq_smem_bytes(int mode, int warps, int smem_per_warp)
+{
+    return (mode == 2 ? 0 : (size_t)warps * FBQ_TILE_BYTES) + (size_t)warps * smem_per_warp;
+}
+
+SweepQPlan sweepq_plan(int npass, int mode, int D)
+{
+    SweepQPlan q{};
+    q.ok = false;
+    if (npass < 1 || npass > FB_MAX_FUSED_PASSES || D < FBQ_U) return q;
+    q.R = (D + FBQ_U - 1) / FBQ_U * FBQ_U;
+    q.RP = q.R + (D % FBQ_U ? FBQ_U : 0);
+    const int nr = npass - 1;
+    int nst_want = g_q_nst.load();
+    if (nst_want < 2) nst_want = 2;
+    if (nst_want > FBQ_MAX_STAGES) nst_want = FBQ_MAX_STAGES;
+    for (int warps = (g_q_warps.load() >= 8 ? 8 : 4); warps >= 4; warps -= 4) {
+        const int cols = warps == 8 ? 256 : 512;
+        int nt = cols / (2 * q.RP);
+        if (nt > nr) nt = nr;
+        const int ns = nr - nt;
+        if (ns > 1) continue;
+        for (int nst = nst_want; nst >= 2; --nst) {
+            const size_t off_ring = 128 + (size_t)nst * FBQ_STAGE_BYTES;
+            const size_t per = off_ring + (size_t)ns * q.RP * 256;
+            if (sweepq_smem_bytes(mode, warps, (int)per) > kQSmemLimit) continue;
+            q.ok = true;
+            q.warps = warps; q.ns = ns; q.nst = nst; q.cols_per_warp = cols;
+            q.smem_per_warp = (int)per; q.off_ring = (int)off_ring;
+            return q;
+        }
+    }
+    return q;
+}
+
+// ---- tensor maps (TMA descriptors) of the q sweeps; the driver's encoder is looked up at run time, so the
+// library keeps loading (and exporting its symbols) on machines without a CUDA driver
+typedef CUresult (*FbTensorMapEncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                           const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                           CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+FbTensorMapEncodeTiled tensor_map_encoder()
+{
+    static std::atomic<void *> cached{nullptr};
+    void *fn = cached.load();
+    if (!fn) {
+        cudaDriverEntryPointQueryResult qres = cudaDriverEntryPointSymbolNotFound;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess)
+            fn = nullptr;
+        cudaGetLastError();
+        cached.store(fn);
+    }
+    return (FbTensorMapEncodeTiled)fn;
+}
+
+// fp64 tensor [d2][d1][d0] (d0 contiguous) with row pitches s1, s2 in bytes, box (b0, b1, 1)
+int make_tensor_map(CUtensorMap &m, const void *base, unsigned long long d0, unsigned long long d1, unsigned long long d2,
+                    unsigned long long s1, unsigned long long s2, unsigned b0, unsigned b1, bool swizzle128, bool promote)
+{
+    FbTensorMapEncodeTiled enc = tensor_map_encoder();
+    if (!enc) return fail(FB_ECUDA, "cuTensorMapEncodeTiled is not available from this CUDA driver");
+    const cuuint64_t dims[3] = {d0, d1, d2};
+    const cuuint64_t strides[2] = {s1, s2};
+    const cuuint32_t box[3] = {b0, b1, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<void *>(base), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                           promote ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return fail(FB_ECUDA, "cuTensorMapEncodeTiled failed (%d): dims %llu x %llu x %llu, pitches %llu / %llu", (int)r, d0, d1, d2, s1, s2);
+    return FB_OK;
+}
+
+template <int NPASS, int NS, int MODE>
+int launch_sweepq_t(FbSweepQ p, const SweepQPlan &q, cudaStream_t st)
+{
+    static thread_local bool configured[16] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!configured[dev & 15]) {
+        CUDA_TRY(cudaFuncSetAttribute(fb_sweepq_kernel<NPASS, NS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kQSmemLimit));
+        CUDA_TRY(cudaFuncSetAttribute(fb_sweepq_kernel<NPASS, NS, MODE>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                      cudaSharedmemCarveoutMaxShared));
+        configured[dev & 15] = true;
+    }
+    const long long nitems = p.n_outer * p.n_groups;
+    if (nitems <= 0) return FB_OK;
+    // input: in[outer][k][2 * n_inner], box = 8 rows of one 16-line group
+    CUtensorMap tm_in, tm_out;
+    const unsigned long long row = (unsigned long long)p.n_inner * 16ull;
+    int rc = make_tensor_map(tm_in, p.in, 2ull * p.n_inner, (unsigned long long)p.L, (unsigned long long)p.n_outer, row, row * p.L, 32, FBQ_U,
+                             false, true);
+    if (rc != FB_OK) return rc;
+    if (MODE == 0) {
+        rc = make_tensor_map(tm_out, p.out, 2ull * p.n_inner, (unsigned long long)p.L, (unsigned long long)p.n_outer, row, row * p.L, 32,
+                             FBQ_U, false, false);
+    } else if (MODE == 1) {
+        // transposed: out[outer][inner][2 * L], box = 8 steps (128 bytes, swizzled in shared memory) of 16 lines
+        const unsigned long long orow = (unsigned long long)p.L * 16ull;
+        rc = make_tensor_map(tm_out, p.out, 2ull * p.L, (unsigned long long)p.n_inner, (unsigned long long)p.n_outer, orow,
+                             orow * p.n_inner, 16, 16, true, false);
+    } else {
+        tm_out = tm_in;
+    }
+    if (rc != FB_OK) return rc;
+    const int sms = sm_count(dev);
+    // few items: spread them over the SMs with fewer warps per CTA
+    int warps = q.warps;
+    if (nitems < (long long)sms * warps) {
+        warps = (int)((nitems + sms - 1) / sms);
+        if (warps < 1) warps = 1;
+    }
+    long long grid = (nitems + warps - 1) / warps;
+    if (grid > sms) grid = sms;
+    const size_t smem = sweepq_smem_bytes(MODE, warps, q.smem_per_warp);
+    // tensor memory: the whole SM's 512 columns when two warps share a lane quarter, else what one warp's rings need
+    // (small launches may place several CTAs on one SM)
+    p.tmem_alloc_cols = 32;
+    if (warps > 4) p.tmem_alloc_cols = 512;
+    else
+        while (p.tmem_alloc_cols < (NPASS - 1 - NS) * 2 * q.RP) p.tmem_alloc_cols *= 2;
+    if (getenv("FB_DEBUG"))
+        fprintf(stderr, "[fb] sweepq<%d,%d,%d> warps %d grid %lld smem %zu nst %d R %d RP %d D %d items %lld\n", NPASS, NS, MODE, warps,
+                grid, smem, q.nst, q.R, q.RP, p.D, nitems);
+    CUDA_TRY(cudaMemsetAsync(p.work_counter, 0, sizeof(unsigned long long), st));
+    fb_sweepq_kernel<NPASS, NS, MODE><<<(unsigned)grid, warps * 32, smem, st>>>(p, tm_in, tm_out);
+    LAUNCH_CHECK();
+    return FB_OK;
+}
+
+template <int MODE>
+int launch_sweepq_m(int npass, const FbSweepQ &p, const SweepQPlan &q, cudaStream_t st)
+{
+    switch (npass * 10 + q.ns) {
+    case 10: return launch_sweepq_t<1, 0, MODE>(p, q, st);
+    case 20: return launch_sweepq_t<2, 0, MODE>(p, q, st);
+    case 21: return launch_sweepq_t<2, 1, MODE>(p, q, st);
+    case 30: return launch_sweepq_t<3, 0, MODE>(p, q, st);
+    case 31: return launch_sweepq_t<3, 1, MODE>(p, q, st);
+    case 40: return launch_sweepq_t<4, 0, MODE>(p, q, st);
+    case 41: return launch_sweepq_t<4, 1, MODE>(p, q, st);
+    case 50: return launch_sweepq_t<5, 0, MODE>(p, q, st);
+    case 51: return launch_sweepq_t<5, 1, MODE>(p, q, st);
+    case 60: return launch_sweepq_t<6, 0, MODE>(p, q, st);
+    case 61: return launch_sweepq_t<6, 1, MODE>(p, q, st);
+    }
+    return fail(FB_EINVAL, "unsupported q-sweep configuration: %d passes, %d shared-memory rings", npass, q.ns);
+}
+
+// one axis of the q path: src / dst are grids of interleaved (value, weight) nodes
+int run_sweepq(int mode, int num_iter, const AxisParams &ax, const double *src, double *dst, float *out32, double *out64,
+               const unsigned long long *mm, double csf, long long n_outer, long long L, long long n_inner, cudaStream_t st,
+               SweepCounters &ctr)
+{
+    const int D = 2 * ax.T + 2;
+    const SweepQPlan q = sweepq_plan(num_iter, mode, D);
+    if (!q.ok) return fail(FB_EKERNEL, "internal: the q sweep does not cover T=%d, num_iter=%d", ax.T, num_iter);
+    if (L > 2147483647LL - 8 * (long long)(ax.T + 1) - 64) return fail(FB_EINVAL, "line too long: %lld", L);
+    FbSweepQ p{};
+    p.in = src; p.out = dst; p.out32 = out32; p.out64 = out64; p.mm = mm;
+    p.n_outer = n_outer; p.L = L; p.n_inner = n_inner; p.n_groups = (n_inner + 15) / 16;
+    p.T = ax.T; p.D = D; p.R = q.R; p.RP = q.RP;
+    p.alpha = ax.alpha; p.csf = csf;
+    p.work_counter = ctr.base + (ctr.next++ % kSweepCounterSlots);
+    p.nst = q.nst; p.pf = g_q_pf.load();
+    p.tmem_cols_per_warp = q.cols_per_warp;
+    p.smem_per_warp = q.smem_per_warp; p.off_ring = q.off_ring;
+    if (mode == 0) return launch_sweepq_m<0>(num_iter, p, q, st);
+    if (mode == 1) return launch_sweepq_m<1>(num_iter, p, q, st);
+    return launch_sweepq_m<2>(num_iter, p, q, st);
 }
 
 // ---- fp32 working precision (FB_FLAG_FP32): fb_sweep32_kernel ------------------------------------------------
@@ -881,8 +1070,23 @@ int run_inject(const fb_problem *pr, const Derived &d, long long nsamples, const
 
 // The fp64 injection writes interleaved (value, weight) nodes when the x sweep that consumes them is the
 // hybrid kernel in a single launch (2D / 3D whole-grid path only; the z-slab path keeps planes).
+// The q path (fb_sweepq.cuh) runs every axis of a 2D / 3D fp64 grid on interleaved nodes; it needs a kernel
+// of at least 8 elements (D = 2T+2 >= 8) and on-chip rings on every axis.
+bool use_sweepq(const fb_problem *pr, const Derived &d)
+{
+    if (pr->dim < 2 || (pr->flags & FB_FLAG_FP32) || g_sweepq.load() == 0) return false;
+    // tensor-map coordinates and the kernels' row offsets are 32-bit
+    if (d.W * d.H > (1LL << 28) || (long long)pr->nfields * d.Dz > (1LL << 30)) return false;
+    for (int m = 0; m < pr->dim; ++m) {
+        const int mode = m == 0 ? 1 : (m == pr->dim - 1 ? 2 : 0);
+        if (!sweepq_plan(pr->num_iter, mode, 2 * d.ax[m].T + 2).ok) return false;
+    }
+    return true;
+}
+
 bool inject_interleaved(const fb_problem *pr, const Derived &d)
 {
+    if (use_sweepq(pr, d)) return true;
     if (pr->dim < 2 || (pr->flags & FB_FLAG_FP32) || g_interleaved.load() == 0) return false;
     return sweep_is_single_hybrid(1, pr->num_iter, d.ax[0].T, (long long)pr->nfields * d.Dz, d.H);
 }
@@ -935,11 +1139,34 @@ int run_sweeps(const fb_problem *pr, const Derived &d, Workspace &w, float *d_ou
         if (rc != FB_OK) return rc;
         return prof_mark(5, st);
     }
+    if (use_sweepq(pr, d)) {
+        // interleaved nodes throughout: A (injected, [..][x][y]) -> B (natural order) -> float32 field
+        double *a2 = w.vA, *b2 = w.vB;                   // vB and wB are adjacent: one block of 2 g bytes
+        rc = run_sweepq(1, n, d.ax[0], a2, b2, nullptr, nullptr, w.mm, d.csf, nf * d.Dz, d.W, d.H, st, ctr);
+        if (rc != FB_OK) return rc;
+        if ((rc = prof_mark(3, st)) != FB_OK) return rc;
+        if (pr->dim == 2) {
+            rc = run_sweepq(2, n, d.ax[1], b2, nullptr, d_out, d_out64, w.mm, d.csf, nf, d.H, d.W, st, ctr);
+            if (rc != FB_OK) return rc;
+            return prof_mark(4, st);
+        }
+        // y sweep in place (pass 1 re-reads a row before the last pass overwrites it: needs >= 2 passes)
+        double *c2 = n >= 2 ? b2 : a2;
+        rc = run_sweepq(0, n, d.ax[1], b2, c2, nullptr, nullptr, w.mm, d.csf, nf * d.Dz, d.H, d.W, st, ctr);
+        if (rc != FB_OK) return rc;
+        if ((rc = prof_mark(4, st)) != FB_OK) return rc;
+        rc = run_sweepq(2, n, d.ax[2], c2, nullptr, d_out, d_out64, w.mm, d.csf, nf, d.Dz, d.H * d.W, st, ctr);
+        if (rc != FB_OK) return rc;
+        return prof_mark(5, st);
+    }
     // x sweep: A layout [..][x][y] -> natural layout [..][y][x]
     if (inject_interleaved(pr, d)) cur = Pair{w.vA, w.vA + 1};       // interleaved (value, weight) nodes
     rc = run_sweep(1, n, d.ax[0], cur, spare, nullptr, nullptr, w.mm, d.csf, nf * d.Dz, d.W, d.H, true, st, ctr,
                    inject_interleaved(pr, d));
     if (rc != FB_OK) return rc;
+    // the A block is free now; later launches that are not in place write PLANES into it (the interleaved alias
+    // {vA, vA + 1} the x sweep read must not survive as an output pair)
+    spare = (cur.v == w.vB) ? Pair{w.vA, w.wA} : Pair{w.vB, w.wB};
     if ((rc = prof_mark(3, st)) != FB_OK) return rc;
     if (pr->dim == 2) {
         rc = run_sweep(2, n, d.ax[1], cur, spare, d_out, d_out64, w.mm, d.csf, nf, d.H, d.W, true, st, ctr);
@@ -1900,6 +2127,10 @@ FB_EXPORT int fb_set_option(const char *name, int value)
     if (!strcmp(name, "interleaved_inject")) { g_interleaved.store(value); return FB_OK; }
     if (!strcmp(name, "inject_lists")) { g_inject_lists.store(value); return FB_OK; }
     if (!strcmp(name, "host_chunk_fields")) { g_host_chunk_fields.store(value); return FB_OK; }
+    if (!strcmp(name, "sweepq")) { g_sweepq.store(value); return FB_OK; }
+    if (!strcmp(name, "sweepq_stages")) { g_q_nst.store(value); return FB_OK; }
+    if (!strcmp(name, "sweepq_prefetch")) { g_q_pf.store(value); return FB_OK; }
+    if (!strcmp(name, "sweepq_warps")) { g_q_warps.store(value); return FB_OK; }
     return fail(FB_EINVAL, "unknown option: %s", name);
 }
 

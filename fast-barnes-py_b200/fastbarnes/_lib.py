@@ -97,17 +97,48 @@ SIGNATURES = {
 }
 
 
+def _source_files():
+    """ Everything the shared library is compiled from. """
+    files = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith(('.cu', '.cuh')) or f == 'Makefile']
+    files.append(os.path.normpath(os.path.join(CSRC, '..', '..', 'include', 'fastbarnes_b200.h')))
+    return files
+
+
+def _source_digest():
+    import hashlib
+    h = hashlib.sha256()
+    for f in _source_files():
+        h.update(os.path.basename(f).encode())
+        with open(f, 'rb') as fh:
+            h.update(fh.read())
+    return h.hexdigest()
+
+
+def _stamp_path():
+    return os.path.join(os.path.dirname(LIB_PATH), 'sources.sha256')
+
+
+def is_stale():
+    """ True when the shared library is missing or was built from other sources (content hash, not mtimes:
+    a copied tree keeps its binary, an edited kernel never runs a stale one). """
+    if not os.path.exists(LIB_PATH):
+        return True
+    try:
+        with open(_stamp_path()) as f:
+            return f.read().strip() != _source_digest()
+    except OSError:
+        return True
+
+
 def build(force=False):
-    """ Compiles csrc/ for sm_100a with nvcc (in-tree, csrc/_build/). """
-    srcs = [os.path.join(CSRC, f) for f in ('fb_api.cu', 'fb_kernels.cuh')]
-    srcs.append(os.path.normpath(os.path.join(CSRC, '..', '..', 'include', 'fastbarnes_b200.h')))
-    stale = (not os.path.exists(LIB_PATH)) or any(
-        os.path.exists(s) and os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)
-    if force or stale:
+    """ Compiles csrc/ for sm_100a with nvcc (in-tree, csrc/_build/) when the sources changed. """
+    if force or is_stale():
         nvcc = shutil.which('nvcc') or '/usr/local/cuda/bin/nvcc'
         if not os.path.exists(nvcc):
             raise RuntimeError('libfastbarnes_b200.so is missing or stale and nvcc was not found to build it')
-        subprocess.check_call(['make', '-C', CSRC, '-s', 'NVCC=' + nvcc] + (['-B'] if force else []))
+        subprocess.check_call(['make', '-C', CSRC, '-s', '-B', 'NVCC=' + nvcc])
+        with open(_stamp_path(), 'w') as f:
+            f.write(_source_digest() + '\n')
     return LIB_PATH
 
 
@@ -118,8 +149,8 @@ def lib():
     """ Returns the loaded shared library with argument types set (loads / builds on first use). """
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
-            build()
+        if os.environ.get('FB_LIB_PATH') is None:
+            build()                                  # no-op unless the sources changed since the last build
         try:
             L = ctypes.CDLL(LIB_PATH)
         except OSError as e:
@@ -139,6 +170,10 @@ def lib():
             L.fb_set_option(b'tmem_sweeps', int(os.environ['FB_TMEM_SWEEPS']))
         if os.environ.get('FB_HOST_CHUNK_FIELDS') is not None:
             L.fb_set_option(b'host_chunk_fields', int(os.environ['FB_HOST_CHUNK_FIELDS']))
+        for env, opt in (('FB_SWEEPQ', b'sweepq'), ('FB_SWEEPQ_STAGES', b'sweepq_stages'),
+                         ('FB_SWEEPQ_PREFETCH', b'sweepq_prefetch'), ('FB_SWEEPQ_WARPS', b'sweepq_warps')):
+            if os.environ.get(env) is not None:
+                L.fb_set_option(opt, int(os.environ[env]))
         _lib = L
     return _lib
 
