@@ -35,9 +35,12 @@
 #include <cuda.h>   // CUtensorMap (types only: the encoder is looked up at run time)
 
 #define FBQ_U 8                 // steps per chunk
-#define FBQ_STAGE_BYTES 4096    // one staging slot: 8 new rows + 8 old rows of 256 bytes
+#define FBQ_STAGE_BYTES 4096    // one staging slot: 8 new rows + 8 old rows of 256 bytes (16 lines x 2 fields x 8 B)
 #define FBQ_TILE_BYTES 2048     // output tile of a warp (MODE 0: 8 rows x 256 B; MODE 1: 16 lines x 128 B, 128B-swizzled)
 #define FBQ_MAX_STAGES 8
+#ifndef FBQ_ST_X2
+#define FBQ_ST_X2 1            // tensor-memory ring stores: 0 = one x16 store per ring and chunk (16 packing moves), 1 = eight x2 stores (measured: x 1.17 -> 1.14 ms, y 1.26 -> 1.20 ms)
+#endif
 
 struct FbSweepQ {
     const double *in;            // interleaved nodes: in[((outer * L + k) * n_inner + inner) * 2 + field]
@@ -49,7 +52,7 @@ struct FbSweepQ {
     int T, D, R, RP;             // RP: physical ring slots (R, or R + 8 with the mirror)
     double alpha, csf;
     unsigned long long *work_counter;
-    int nst;                     // staging slots per warp (chunks in flight), 2..FBQ_MAX_STAGES
+    int nst;                     // staging slots per warp (chunks in flight), 2..FBQ_MAX_STAGES; a slot = 8 new + 8 old rows
     int pf;                      // extra chunks of lead of an L2 prefetch of the new rows (0: none)
     int tmem_cols_per_warp;      // tensor-memory columns of one warp (two warps share a lane quarter when 8 warps run)
     int tmem_alloc_cols;         // columns the CTA allocates (power of two >= 32; 512 when more than 4 warps run)
@@ -79,26 +82,51 @@ __device__ __forceinline__ void fbq_mbar_wait(unsigned bar, unsigned parity)
         "FBQ_DONE:\n"
         "}\n" ::"r"(bar), "r"(parity) : "memory");
 }
-// TMA tensor load of one box (32 doubles x 8 rows x 1) at (c0, c1, c2); completion counted in bytes on the mbarrier
-__device__ __forceinline__ void fbq_tma_load(unsigned dst, const CUtensorMap *tm, int c0, int c1, int c2, unsigned bar)
+// The requests of one chunk, by one elected lane of the (converged) warp: arm the stage's mbarrier with the bytes of
+// both boxes, then two TMA tensor loads of a box of 32 doubles x 8 rows: rows c1n .. c1n+7 to dst, rows c1o .. c1o+7
+// to dst + 2 KB.  The election sits inside the asm so that the compiler sees one convergent statement (a C++ `if
+// (lane == 0)` around it costs an ELECT / BRA.U.ANY loop per instruction).
+__device__ __forceinline__ void fbq_issue_chunk(unsigned dst, const CUtensorMap *tm, int c0, int c1n, int c1o, int c2, unsigned bar,
+                                                int enable)
 {
-    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-                 ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
+    asm volatile(
+        "{\n"
+        ".reg .pred p, q;\n"
+        ".reg .b32 d2;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "setp.ne.b32 q, %7, 0;\n"
+        "and.pred p, p, q;\n"
+        "add.u32 d2, %0, 2048;\n"
+        "@p mbarrier.arrive.expect_tx.shared::cta.b64 _, [%6], 4096;\n"
+        "@p cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %5}], [%6];\n"
+        "@p cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [d2], [%1, {%2, %4, %5}], [%6];\n"
+        "}\n" ::"r"(dst), "l"(tm), "r"(c0), "r"(c1n), "r"(c1o), "r"(c2), "r"(bar), "r"(enable) : "memory");
 }
 __device__ __forceinline__ void fbq_tma_prefetch(const CUtensorMap *tm, int c0, int c1, int c2)
 {
     asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(tm), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
-// TMA tensor store of one box from shared memory (bulk async-group completion); out-of-bounds parts are clipped
+// TMA tensor store of one box from shared memory by one elected lane + commit of its bulk async-group (every lane
+// commits: an empty group for the others); out-of-bounds parts of the box are clipped
 __device__ __forceinline__ void fbq_tma_store(const CUtensorMap *tm, int c0, int c1, int c2, unsigned src)
 {
-    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(tm), "r"(c0), "r"(c1),
-                 "r"(c2), "r"(src) : "memory");
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "@p cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3}], [%4];\n"
+        "cp.async.bulk.commit_group;\n"
+        "}\n" ::"l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(src) : "memory");
 }
 __device__ __forceinline__ void fbq_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void fbq_bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fbq_bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fbq_fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void fbq_tmem_st2(unsigned taddr, unsigned r0, unsigned r1)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr), "r"(r0), "r"(r1) : "memory");
+}
 
 __device__ __forceinline__ double fbq_lds(unsigned addr)
 {
@@ -144,36 +172,84 @@ __device__ __forceinline__ void fbq_chunk(const double (&bn)[FBQ_U], const doubl
     }
     unsigned newt[NT > 0 ? NT : 1][16];
     double news[NS > 0 ? NS : 1][U];
+    if constexpr (!MASKED) {
 #pragma unroll
-    for (int j = 0; j < U; ++j) {
-        double x = bn[j];
+        for (int j = 0; j < U; ++j) {
+            double x = bn[j];
+#pragma unroll
+            for (int q = 0; q < NPASS; ++q) {
+                double o;
+                if (q == 0) {
+                    o = bo[j];
+                } else if (q - 1 < NS) {
+                    o = olds[q - 1 < NS ? q - 1 : 0][j];
+                    news[q - 1 < NS ? q - 1 : 0][j] = x;
+                } else {
+                    const int r = q - 1 - NS;
+                    o = __hiloint2double((int)oldt[r >= 0 ? r : 0][2 * j + 1], (int)oldt[r >= 0 ? r : 0][2 * j]);
+                    newt[r >= 0 ? r : 0][2 * j] = (unsigned)__double2loint(x);
+                    newt[r >= 0 ? r : 0][2 * j + 1] = (unsigned)__double2hiint(x);
+                }
+                // interpolation.py:512-514 with zero extension: accu += in[k+T] - in[k-T-1];
+                // out[k] = accu + alpha * (in[k-T-1] + in[k+T+1])
+                const double d = __dsub_rn(new0[q], o);
+                accu[q] = __dadd_rn(accu[q], d);
+                const double r = __dadd_rn(accu[q], __dmul_rn(alpha, __dadd_rn(o, x)));
+                new0[q] = x;
+                x = r;
+            }
+            xs[j] = x;
+        }
+    } else {
+        // line ends, pass by pass: the same operations; results at positions outside [0, L) are replaced by zeros
+        // (zero extension of every pass's output), and a pass whose input has not begun (start of the line) or
+        // whose output positions all lie beyond the line (end of the line) is skipped -- its result is zeros.
+        double xin[U];
+#pragma unroll
+        for (int j = 0; j < U; ++j) xin[j] = bn[j];
 #pragma unroll
         for (int q = 0; q < NPASS; ++q) {
-            double o;
-            if (q == 0) {
-                o = bo[j];
-            } else if (q - 1 < NS) {
-                o = olds[q - 1 < NS ? q - 1 : 0][j];
-                news[q - 1 < NS ? q - 1 : 0][j] = x;
+            if (q >= 1) {
+#pragma unroll
+                for (int j = 0; j < U; ++j) {
+                    if (q - 1 < NS) {
+                        news[q - 1 < NS ? q - 1 : 0][j] = xin[j];
+                    } else {
+                        const int r = q - 1 - NS;
+                        newt[r >= 0 ? r : 0][2 * j] = (unsigned)__double2loint(xin[j]);
+                        newt[r >= 0 ? r : 0][2 * j + 1] = (unsigned)__double2hiint(xin[j]);
+                    }
+                }
+            }
+            const int k0 = t - (q + 1) * T1;             // output position of step 0 of this pass
+            const bool active = (t + U - 1 >= q * T1) && (k0 < L);
+            if (active) {
+#pragma unroll
+                for (int j = 0; j < U; ++j) {
+                    double o;
+                    if (q == 0) {
+                        o = bo[j];
+                    } else if (q - 1 < NS) {
+                        o = olds[q - 1 < NS ? q - 1 : 0][j];
+                    } else {
+                        const int r = q - 1 - NS;
+                        o = __hiloint2double((int)oldt[r >= 0 ? r : 0][2 * j + 1], (int)oldt[r >= 0 ? r : 0][2 * j]);
+                    }
+                    const double x = xin[j];
+                    const double d = __dsub_rn(new0[q], o);
+                    accu[q] = __dadd_rn(accu[q], d);
+                    const double r = __dadd_rn(accu[q], __dmul_rn(alpha, __dadd_rn(o, x)));
+                    new0[q] = x;
+                    const int k = k0 + j;
+                    xin[j] = (k >= 0 && k < L) ? r : 0.0;
+                }
             } else {
-                const int r = q - 1 - NS;
-                o = __hiloint2double((int)oldt[r >= 0 ? r : 0][2 * j + 1], (int)oldt[r >= 0 ? r : 0][2 * j]);
-                newt[r >= 0 ? r : 0][2 * j] = (unsigned)__double2loint(x);
-                newt[r >= 0 ? r : 0][2 * j + 1] = (unsigned)__double2hiint(x);
+#pragma unroll
+                for (int j = 0; j < U; ++j) xin[j] = 0.0;
             }
-            // interpolation.py:512-514 with zero extension: accu += in[k+T] - in[k-T-1];
-            // out[k] = accu + alpha * (in[k-T-1] + in[k+T+1])
-            const double d = __dsub_rn(new0[q], o);
-            accu[q] = __dadd_rn(accu[q], d);
-            double r = __dadd_rn(accu[q], __dmul_rn(alpha, __dadd_rn(o, x)));
-            new0[q] = x;
-            if (MASKED) {
-                const int k = t + j - (q + 1) * T1;
-                r = (k >= 0 && k < L) ? r : 0.0;
-            }
-            x = r;
         }
-        xs[j] = x;
+#pragma unroll
+        for (int j = 0; j < U; ++j) xs[j] = xin[j];
     }
     if constexpr (NS > 0) {
 #pragma unroll
@@ -189,12 +265,27 @@ __device__ __forceinline__ void fbq_chunk(const double (&bn)[FBQ_U], const doubl
         }
     }
     if constexpr (NT > 0) {
+#if FBQ_ST_X2
+        // one 64-bit store per slot: the operands are the register pairs the passes produced (no packing moves)
+#pragma unroll
+        for (int q = 0; q < NT; ++q)
+#pragma unroll
+            for (int j = 0; j < U; ++j) fbq_tmem_st2(tw + (unsigned)q * rp_cols + 2u * (unsigned)j, newt[q][2 * j], newt[q][2 * j + 1]);
+        if (mirror) {
+#pragma unroll
+            for (int q = 0; q < NT; ++q)
+#pragma unroll
+                for (int j = 0; j < U; ++j)
+                    fbq_tmem_st2(tw + (unsigned)q * rp_cols + 2u * mirror_slots + 2u * (unsigned)j, newt[q][2 * j], newt[q][2 * j + 1]);
+        }
+#else
 #pragma unroll
         for (int q = 0; q < NT; ++q) fb_tmem_st16(tw + (unsigned)q * rp_cols, newt[q]);
         if (mirror) {
 #pragma unroll
             for (int q = 0; q < NT; ++q) fb_tmem_st16(tw + (unsigned)q * rp_cols + 2u * mirror_slots, newt[q]);
         }
+#endif
     }
 }
 
@@ -250,7 +341,9 @@ fb_sweepq_kernel(const FbSweepQ p, const __grid_constant__ CUtensorMap tm_in, co
     __shared__ unsigned s_tmem_base;
 
     const int lane = threadIdx.x & 31;
-    const int wid = threadIdx.x >> 5;
+    // warp index through redux.sync: the result lives in a uniform register, so everything derived from it (shared-memory
+    // addresses of the TMA operations) is uniform for the compiler and UTMALDG / UTMASTG need no per-lane loop
+    const int wid = __reduce_max_sync(0xffffffffu, (int)(threadIdx.x >> 5));
     const int nwarps = blockDim.x >> 5;
 
     if constexpr (NT > 0) {
@@ -265,10 +358,11 @@ fb_sweepq_kernel(const FbSweepQ p, const __grid_constant__ CUtensorMap tm_in, co
     const unsigned tile = sm0 + (unsigned)wid * FBQ_TILE_BYTES;
     const unsigned wsm = sm0 + (MODE == 2 ? 0u : (unsigned)nwarps * FBQ_TILE_BYTES) + (unsigned)wid * (unsigned)p.smem_per_warp;
     const unsigned bars = wsm;
-    const unsigned stages = wsm + 128u;
-    const unsigned ring_s = wsm + (unsigned)p.off_ring + (unsigned)lane * 8u;
     const int nst = p.nst;
+    const unsigned stages = wsm + 128u;                                    // nst slots of 4 KB
+    const unsigned ring_s = wsm + (unsigned)p.off_ring + (unsigned)lane * 8u;
     if (lane == 0) {
+        // one mbarrier per chunk in flight; a phase = the two boxes of a chunk (new rows, old rows), 2 KB each
         for (int s = 0; s < nst; ++s) fbq_mbar_init(bars + 8u * (unsigned)s, 1u);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -301,12 +395,17 @@ fb_sweepq_kernel(const FbSweepQ p, const __grid_constant__ CUtensorMap tm_in, co
 
 #pragma unroll 1
     for (;;) {
-        unsigned long long claimed = 0;
-        if (lane == 0) claimed = atomicAdd(p.work_counter, 1ull);
-        claimed = __shfl_sync(0xffffffffu, claimed, 0);
-        if ((long long)claimed >= n_items) break;
-        const int outer = (int)((long long)claimed / p.n_groups);
-        const int group = (int)((long long)claimed - (long long)outer * p.n_groups);
+        // claim a 16-line group; item, outer and group go through redux.sync as well (uniform registers)
+        int it = 0, ou = 0, gr = 0;
+        if (lane == 0) {
+            const unsigned long long claimed = atomicAdd(p.work_counter, 1ull);
+            it = claimed < (unsigned long long)n_items ? (int)claimed : 0x7fffffff;
+            ou = (int)((long long)it / p.n_groups);
+            gr = (int)((long long)it - (long long)ou * p.n_groups);
+        }
+        if (__reduce_max_sync(0xffffffffu, it) == 0x7fffffff) break;
+        const int outer = __reduce_max_sync(0xffffffffu, ou);
+        const int group = __reduce_max_sync(0xffffffffu, gr);
         const long long inner = (long long)group * 16 + (lane >> 1);
 
         // rings start as zeros (zero extension to the left of the line)
@@ -322,23 +421,15 @@ fb_sweepq_kernel(const FbSweepQ p, const __grid_constant__ CUtensorMap tm_in, co
         }
         __syncwarp();
 
-        // request the rows of the chunk at stream position tt into staging slot `slot`: the 8 newest rows
-        // tt .. tt+7 and the 8 rows tt-D .. tt-D+7 (rows outside [0, L) arrive as zeros)
-        auto issue = [&](int tt, int slot) {
-            if (lane == 0) {
-                const unsigned st = stages + (unsigned)slot * FBQ_STAGE_BYTES;
-                const unsigned bar = bars + 8u * (unsigned)slot;
-                fbq_mbar_expect_tx(bar, FBQ_STAGE_BYTES);
-                fbq_tma_load(st, &tm_in, group * 32, tt, outer, bar);
-                fbq_tma_load(st + 2048u, &tm_in, group * 32, tt - D, outer, bar);
-                if (p.pf > 0 && tt + p.pf * U < L) fbq_tma_prefetch(&tm_in, group * 32, tt + p.pf * U, outer);
-            }
+        // requests of the chunk at stream position tt: the 8 newest rows tt .. tt+7 and the 8 rows tt-D .. tt-D+7
+        // (rows outside [0, L) arrive as zeros) into staging slot sl
+        auto issue = [&](int tt, int sl, int enable) {
+            fbq_issue_chunk(stages + (unsigned)sl * FBQ_STAGE_BYTES, &tm_in, group * 32, tt, tt - D, outer, bars + 8u * (unsigned)sl,
+                            enable);
+            if (p.pf > 0 && lane == 0 && enable && tt + p.pf * U < L) fbq_tma_prefetch(&tm_in, group * 32, tt + p.pf * U, outer);
         };
 
-        {
-            const int npro = nst < nchunks ? nst : nchunks;
-            for (int c = 0; c < npro; ++c) issue(t_begin + c * U, c);
-        }
+        for (int c = 0; c < nst; ++c) issue(t_begin + c * U, c, c < nchunks);
 
         double accu[NPASS], new0[NPASS];
 #pragma unroll
@@ -346,73 +437,86 @@ fb_sweepq_kernel(const FbSweepQ p, const __grid_constant__ CUtensorMap tm_in, co
         double offset = 0.0;
         if (MODE == 2) offset = fb_field_offset(p.mm, outer);
 
+        // output of the 8 rows kb .. kb+7 that left the last pass one chunk ago (kb is a multiple of 8, 0 <= kb < L;
+        // all_rows: kb + 7 < L)
+        auto emit = [&](const double (&x)[U], int kb, bool all_rows) {
+            if (MODE == 0 || MODE == 1) {
+                fbq_bulk_wait_read0();                               // the previous tile has been read (whichever lane stored it)
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < U; ++j)
+                    fbq_sts(MODE == 1 ? tile_lane + (((unsigned)j << 4) ^ tile_xor) : tile_lane + (unsigned)j * 256u, x[j]);
+                fbq_fence_async();
+                __syncwarp();
+                if (MODE == 1) fbq_tma_store(&tm_out, 2 * kb, group * 16, outer, tile);
+                else fbq_tma_store(&tm_out, group * 32, kb, outer, tile);
+            } else {
+                unsigned rows = 0;
+                if (inner < p.n_inner) {
+                    if (all_rows) {
+                        rows = 15u;
+                    } else {
+#pragma unroll
+                        for (int m = 0; m < U / 2; ++m)
+                            if (kb + 2 * m + fld < L) rows |= 1u << m;
+                    }
+                }
+                const long long o = ((long long)outer * p.L + kb + fld) * p.n_inner + inner;
+                fbq_finalize_chunk(x, fld, p.csf, offset, p.out32 + o, p.out64 ? p.out64 + o : nullptr, (unsigned)p.n_inner, rows);
+            }
+        };
+
         int wslot = 0;                                   // ring write slot of this chunk (multiple of 8)
         int rslot = (R - D % R) % R;                     // ring read slot: (wslot - D) mod R
         int slot = 0;                                    // staging slot of this chunk
         int t = t_begin;
+        // The loop is rotated: iteration c runs the passes of chunk c AND writes out the rows chunk c-1 produced, in one
+        // basic block on the fast path, so that the divisions / tile stores of the output (long dependency chains, few
+        // instructions) overlap with the dense fp64 stream of the passes.
+        double xsp[U];
+#pragma unroll
+        for (int j = 0; j < U; ++j) xsp[j] = 0.0;
 #pragma unroll 1
         for (int c = 0; c < nchunks; ++c, t += U) {
-            const unsigned st = stages + (unsigned)slot * FBQ_STAGE_BYTES + (unsigned)lane * 8u;
+            const unsigned stn = stages + (unsigned)slot * FBQ_STAGE_BYTES + (unsigned)lane * 8u;
+            const unsigned sto = stn + 2048u;
             fbq_mbar_wait(bars + 8u * (unsigned)slot, (phases >> slot) & 1u);
             phases ^= 1u << slot;
             double bn[U], bo[U], xs[U];
 #pragma unroll
-            for (int j = 0; j < U; ++j) bn[j] = fbq_lds(st + (unsigned)j * 256u);
+            for (int j = 0; j < U; ++j) bn[j] = fbq_lds(stn + (unsigned)j * 256u);
 #pragma unroll
-            for (int j = 0; j < U; ++j) bo[j] = fbq_lds(st + 2048u + (unsigned)j * 256u);
+            for (int j = 0; j < U; ++j) bo[j] = fbq_lds(sto + (unsigned)j * 256u);
             const unsigned sr = ring_s + (unsigned)rslot * 256u, sw = ring_s + (unsigned)wslot * 256u;
             const unsigned tr = tring + 2u * (unsigned)rslot, tw = tring + 2u * (unsigned)wslot;
             const bool mirror = has_mirror && wslot == 0;
-            const bool interior = (t >= lag) && (t + U - 1 - T1 < L);
-            const int kb = t - lag;                      // rows kb .. kb+7 leave the last pass (kb is a multiple of 8)
-            if (interior) {
+            // fast path: every pass position of this chunk and every row of the previous chunk's output inside the line
+            const bool fast = (t - U >= lag) && (t + U - 1 - T1 < L);
+            const int kbp = t - U - lag;                 // rows kbp .. kbp+7 left the last pass in the previous chunk
+            if (fast) {
                 fbq_chunk<NPASS, NS, false>(bn, bo, accu, new0, xs, sr, sw, rp_bytes, tr, tw, rp_cols, mirror, (unsigned)R, t, T1, L, alpha);
+                emit(xsp, kbp, true);
             } else {
                 fbq_chunk<NPASS, NS, true>(bn, bo, accu, new0, xs, sr, sw, rp_bytes, tr, tw, rp_cols, mirror, (unsigned)R, t, T1, L, alpha);
-            }
-            // ---- output of rows kb .. kb+7 (those inside the line)
-            if (kb >= 0 && kb < L) {
-                if (MODE == 0 || MODE == 1) {
-                    if (lane == 0) fbq_bulk_wait_read0();            // the previous tile has been read
-                    __syncwarp();
-#pragma unroll
-                    for (int j = 0; j < U; ++j)
-                        fbq_sts(MODE == 1 ? tile_lane + (((unsigned)j << 4) ^ tile_xor) : tile_lane + (unsigned)j * 256u, xs[j]);
-                    fbq_fence_async();
-                    __syncwarp();
-                    if (lane == 0) {
-                        if (MODE == 1) fbq_tma_store(&tm_out, 2 * kb, group * 16, outer, tile);
-                        else fbq_tma_store(&tm_out, group * 32, kb, outer, tile);
-                        fbq_bulk_commit();
-                    }
-                } else {
-                    unsigned rows = 0;
-                    if (inner < p.n_inner) {
-                        if (interior) {
-                            rows = 15u;
-                        } else {
-#pragma unroll
-                            for (int m = 0; m < U / 2; ++m)
-                                if (kb + 2 * m + fld < L) rows |= 1u << m;
-                        }
-                    }
-                    const long long o = ((long long)outer * p.L + kb + fld) * p.n_inner + inner;
-                    fbq_finalize_chunk(xs, fld, p.csf, offset, p.out32 + o, p.out64 ? p.out64 + o : nullptr, (unsigned)p.n_inner, rows);
-                }
+                if (kbp >= 0 && kbp < L) emit(xsp, kbp, false);
             }
             // ---- the staging slot is free: request the chunk nst chunks ahead
             __syncwarp();
-            if (c + nst < nchunks) issue(t + nst * U, slot);
+            issue(t + nst * U, slot, c + nst < nchunks);
             if constexpr (NT > 0) fb_tmem_wait_st();
+#pragma unroll
+            for (int j = 0; j < U; ++j) xsp[j] = xs[j];
             wslot += U; wslot = (wslot >= R) ? 0 : wslot;
             rslot += U; rslot = (rslot >= R) ? rslot - R : rslot;
             ++slot; slot = (slot == nst) ? 0 : slot;
         }
+        {
+            const int kbp = t - U - lag;                 // the rows of the last chunk
+            if (kbp >= 0 && kbp < L) emit(xsp, kbp, false);
+        }
     }   // persistent loop
 
-    if (MODE == 0 || MODE == 1) {
-        if (lane == 0) fbq_bulk_wait0();
-    }
+    if (MODE == 0 || MODE == 1) fbq_bulk_wait0();
     if constexpr (NT > 0) {
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();

@@ -130,6 +130,12 @@ def is_stale():
         return True
 
 
+def mark_built():
+    """ Records that LIB_PATH was just built from the current sources (after a manual `make`). """
+    with open(_stamp_path(), 'w') as f:
+        f.write(_source_digest() + '\n')
+
+
 def build(force=False):
     """ Compiles csrc/ for sm_100a with nvcc (in-tree, csrc/_build/) when the sources changed. """
     if force or is_stale():
@@ -137,8 +143,7 @@ def build(force=False):
         if not os.path.exists(nvcc):
             raise RuntimeError('libfastbarnes_b200.so is missing or stale and nvcc was not found to build it')
         subprocess.check_call(['make', '-C', CSRC, '-s', '-B', 'NVCC=' + nvcc])
-        with open(_stamp_path(), 'w') as f:
-            f.write(_source_digest() + '\n')
+        mark_built()
     return LIB_PATH
 
 

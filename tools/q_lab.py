@@ -123,16 +123,14 @@ def timing(settings=None):
     d_val = torch.from_numpy(val_h.reshape(F * bench.N_PER_FIELD)).cuda()
     plan = fbi.BarnesDevice(2, bench.SIGMA, bench.X0, bench.STEP, bench.SIZE, nfields=F, nsamples=F * bench.N_PER_FIELD,
                             num_iter=bench.NUM_ITER)
+    if settings is None and os.environ.get('QLAB_SETTINGS'):
+        settings = json.loads(os.environ['QLAB_SETTINGS'])
     if settings is None:
         settings = [
             dict(sweepq=0),
             dict(sweepq=1, sweepq_stages=3, sweepq_prefetch=0, sweepq_warps=8),
             dict(sweepq=1, sweepq_stages=2, sweepq_prefetch=0, sweepq_warps=8),
-            dict(sweepq=1, sweepq_stages=3, sweepq_prefetch=2, sweepq_warps=8),
-            dict(sweepq=1, sweepq_stages=3, sweepq_prefetch=4, sweepq_warps=8),
-            dict(sweepq=1, sweepq_stages=2, sweepq_prefetch=4, sweepq_warps=8),
-            dict(sweepq=1, sweepq_stages=4, sweepq_prefetch=0, sweepq_warps=4),
-            dict(sweepq=1, sweepq_stages=6, sweepq_prefetch=0, sweepq_warps=4),
+            dict(sweepq=1, sweepq_stages=3, sweepq_prefetch=5, sweepq_warps=8),
         ]
     ref = None
     results = []
@@ -145,7 +143,7 @@ def timing(settings=None):
         torch.cuda.synchronize()
         L.fb_set_profiling(1)
         acc = np.zeros(5)
-        steps = 10
+        steps = int(os.environ.get('QLAB_STEPS', '10'))
         for _ in range(steps):
             out = plan(d_pts, d_val)
             _lib.check(L.fb_last_profile(seg.ctypes.data_as(_lib.c_double_p), 5, nl.ctypes.data_as(_lib.c_i64_p)))
