@@ -216,6 +216,10 @@ int launch_sweep2_t(const FbSweep &p, size_t smem, cudaStream_t st)
 template <int MODE>
 int launch_sweep2_m(int npass, const FbSweep &p, size_t smem, cudaStream_t st)
 {
+#ifdef FBQ_LAB
+    (void)npass;
+    return fail(FB_EKERNEL, "lab build: kernel family compiled out");
+#else
     const int na = sweep2_na(npass, MODE);
     if constexpr (MODE == 2) {
         switch (npass) {
@@ -240,6 +244,7 @@ int launch_sweep2_m(int npass, const FbSweep &p, size_t smem, cudaStream_t st)
         }
     }
     return fail(FB_EINVAL, "unsupported pass split: %d/%d", npass, na);
+#endif
 }
 
 // three-warp kernel: stage split (S0, S1, S2) of npass passes
@@ -305,6 +310,10 @@ int launch_sweep3_t(const FbSweep &p, size_t smem, cudaStream_t st)
 template <int MODE>
 int launch_sweep3_m(int npass, const FbSweep &p, size_t smem, cudaStream_t st)
 {
+#ifdef FBQ_LAB
+    (void)npass;
+    return fail(FB_EKERNEL, "lab build: kernel family compiled out");
+#else
     if constexpr (MODE == 2) {
         switch (npass) {
         case 2: return launch_sweep3_t<1, 1, 0, MODE>(p, smem, st);
@@ -322,6 +331,7 @@ int launch_sweep3_m(int npass, const FbSweep &p, size_t smem, cudaStream_t st)
         }
     }
     return fail(FB_EINVAL, "unsupported three-stage split of %d passes", npass);
+#endif
 }
 
 // hybrid kernel: two two-warp pipelines per CTA, private rings in tensor memory
@@ -395,6 +405,10 @@ int launch_sweeph_t(const FbSweep &p, int npass, cudaStream_t st)
 template <int MODE>
 int launch_sweeph_m(int npass, const FbSweep &p, cudaStream_t st)
 {
+#ifdef FBQ_LAB
+    (void)npass;
+    return fail(FB_EKERNEL, "lab build: kernel family compiled out");
+#else
     switch (npass) {
     case 2: return launch_sweeph_t<1, 1, MODE>(p, npass, st);
     case 3: return launch_sweeph_t<1, 2, MODE>(p, npass, st);
@@ -403,6 +417,7 @@ int launch_sweeph_m(int npass, const FbSweep &p, cudaStream_t st)
     case 6: return launch_sweeph_t<3, 3, MODE>(p, npass, st);
     }
     return fail(FB_EINVAL, "unsupported number of fused passes: %d", npass);
+#endif
 }
 
 int launch_sweeph(int m, int npass, const FbSweep &p, cudaStream_t st)
@@ -556,6 +571,11 @@ int launch_sweepq_t(FbSweepQ p, const SweepQPlan &q, cudaStream_t st)
 template <int MODE>
 int launch_sweepq_m(int npass, const FbSweepQ &p, const SweepQPlan &q, cudaStream_t st)
 {
+#ifdef FBQ_LAB
+    // lab builds (make EXTRA=-DFBQ_LAB): only the q kernels of the bench configuration, for quick A/B variants
+    if (npass == 4 && q.ns == 1) return launch_sweepq_t<4, 1, MODE>(p, q, st);
+    return fail(FB_EKERNEL, "lab build: kernel family compiled out");
+#else
     switch (npass * 10 + q.ns) {
     case 10: return launch_sweepq_t<1, 0, MODE>(p, q, st);
     case 20: return launch_sweepq_t<2, 0, MODE>(p, q, st);
@@ -570,6 +590,7 @@ int launch_sweepq_m(int npass, const FbSweepQ &p, const SweepQPlan &q, cudaStrea
     case 61: return launch_sweepq_t<6, 1, MODE>(p, q, st);
     }
     return fail(FB_EINVAL, "unsupported q-sweep configuration: %d passes, %d shared-memory rings", npass, q.ns);
+#endif
 }
 
 // one axis of the q path: src / dst are grids of interleaved (value, weight) nodes
@@ -650,6 +671,10 @@ int launch_sweep32_t(FbSweep32 p, cudaStream_t st)
 template <int MODE>
 int launch_sweep32_m(int npass, const FbSweep32 &p, cudaStream_t st)
 {
+#ifdef FBQ_LAB
+    (void)npass;
+    return fail(FB_EKERNEL, "lab build: kernel family compiled out");
+#else
     switch (npass) {
     case 1: return launch_sweep32_t<1, MODE>(p, st);
     case 2: return launch_sweep32_t<2, MODE>(p, st);
@@ -659,6 +684,7 @@ int launch_sweep32_m(int npass, const FbSweep32 &p, cudaStream_t st)
     case 6: return launch_sweep32_t<6, MODE>(p, st);
     }
     return fail(FB_EINVAL, "unsupported number of fused passes: %d", npass);
+#endif
 }
 
 // one axis of the fp32 path
@@ -716,6 +742,10 @@ int launch_sweep_t(const FbSweep &p, size_t smem, cudaStream_t st)
 template <int MODE, int U>
 int launch_sweep_u(int npass, const FbSweep &p, size_t smem, cudaStream_t st)
 {
+#ifdef FBQ_LAB
+    (void)npass;
+    return fail(FB_EKERNEL, "lab build: kernel family compiled out");
+#else
     switch (npass) {
     case 1: return launch_sweep_t<1, MODE, U>(p, smem, st);
     case 2: return launch_sweep_t<2, MODE, U>(p, smem, st);
@@ -725,6 +755,7 @@ int launch_sweep_u(int npass, const FbSweep &p, size_t smem, cudaStream_t st)
     case 6: return launch_sweep_t<6, MODE, U>(p, smem, st);
     }
     return fail(FB_EINVAL, "unsupported number of fused passes: %d", npass);
+#endif
 }
 
 template <int MODE>

@@ -128,9 +128,9 @@ def timing(settings=None):
     if settings is None:
         settings = [
             dict(sweepq=0),
-            dict(sweepq=1, sweepq_stages=3, sweepq_prefetch=0, sweepq_warps=8),
-            dict(sweepq=1, sweepq_stages=2, sweepq_prefetch=0, sweepq_warps=8),
-            dict(sweepq=1, sweepq_stages=3, sweepq_prefetch=5, sweepq_warps=8),
+            dict(sweepq=1, sweepq_stages=3, sweepq_finalize_warps=1),
+            dict(sweepq=1, sweepq_stages=3, sweepq_finalize_warps=0),
+            dict(sweepq=1, sweepq_stages=2, sweepq_finalize_warps=1),
         ]
     ref = None
     results = []
@@ -151,6 +151,12 @@ def timing(settings=None):
         L.fb_set_profiling(0)
         acc /= steps
         o = out.cpu().numpy()
+        refp = os.environ.get('QLAB_REF_OUT')
+        if refp and ref is None:
+            if os.path.exists(refp):
+                ref = np.load(refp)                  # the field of the reference build (first setting: gen-1 kernels)
+            else:
+                np.save(refp, o)
         if ref is None:
             ref = o
         rec = dict(st)
@@ -158,7 +164,7 @@ def timing(settings=None):
                     'equal_to_first': bits_equal(o, ref)})
         results.append(rec)
         print(json.dumps(rec), flush=True)
-    set_opts(L, sweepq=1, sweepq_stages=3, sweepq_prefetch=0, sweepq_warps=8)
+    set_opts(L, sweepq=1, sweepq_stages=3, sweepq_finalize_warps=1)
     return results
 
 
