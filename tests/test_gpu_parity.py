@@ -853,3 +853,92 @@ def test_3d_volume_hybrid_kernels(fb, orc):
         assert bits_equal(out, ref), n
     a = fb.barnes(pts, val, 1.0, [0.0, 0.0, 0.0], step, size, num_iter=4, precision='fp32')
     assert fp32_close(a, fb.barnes(pts, val, 1.0, [0.0, 0.0, 0.0], step, size, num_iter=4), float(val.max() - val.min()))
+
+
+# ---------------------------------------------------------------------------------------------
+# second-generation sweep kernels (csrc/fb_sweepq.cuh): one warp = 16 lines x all passes, TMA row staging, rings in tensor
+# and shared memory.  They are the default for 2D / 3D fp64 grids whose kernels have 2T+2 >= 8 elements on every axis.
+
+def _q_option(value):
+    from fastbarnes import _lib
+    _lib.check(_lib.lib().fb_set_option(b'sweepq', value))
+
+
+@pytest.mark.parametrize('dim,size,ratio,nf,iters', [
+    (2, (512, 500), (8.0, 8.0), 4, (1, 2, 3, 4, 5, 6)),     # T = 5..13: 2T+2 no multiple of 8 (ring mirrors), rings in tensor memory
+    (2, (333, 217), (13.0, 9.0), 3, (3, 4)),                # ragged 16-line groups on both axes, anisotropic kernel
+    (2, (1000, 300), (60.0, 5.0), 2, (4,)),                 # T = 51 (four warps per CTA) and T = 3 (2T+2 = 8, the minimum)
+    (2, (640, 400), (40.0, 34.0), 2, (2, 6)),               # T = 48 / 27: two and six passes
+    (3, (160, 128, 96), (6.0, 7.0, 6.5), 1, (1, 2, 4, 5)),  # 3D: transposing x sweep, in-place y sweep, finalising z sweep
+])
+def test_sweepq_vs_first_generation(fb, dim, size, ratio, nf, iters):
+    """ bit for bit against the first-generation kernels (themselves bit-identical to the reference): float32 field and
+    fp64 quotient, samples outside the grid, repeated locations """
+    torch = pytest.importorskip('torch')
+    rng = np.random.default_rng(4242 + dim + len(iters))
+    step = 0.1
+    sigma = [r * step for r in ratio]
+    ext = (np.asarray(size) - 1) * step
+    N = 4000
+    pts = rng.uniform(-0.02, 1.02, (nf, N, dim)) * ext
+    pts[:, :200] = pts[:, 200:400]
+    val = rng.normal(100, 20, (nf, N))
+    d_pts = torch.from_numpy(pts.reshape(nf * N, dim)).cuda()
+    d_val = torch.from_numpy(val.reshape(nf * N)).cuda()
+    for n in iters:
+        plan = fb.BarnesDevice(dim, sigma, [0.0] * dim, step, size, nfields=nf, nsamples=nf * N, num_iter=n, want_float64=True)
+        try:
+            _q_option(1)
+            a, a64 = plan(d_pts, d_val).cpu().numpy(), plan.out64.cpu().numpy()
+            _q_option(0)
+            b, b64 = plan(d_pts, d_val).cpu().numpy(), plan.out64.cpu().numpy()
+        finally:
+            _q_option(1)
+        assert bits_equal(a, b) and bits_equal(a64, b64), (dim, size, n)
+
+
+@pytest.mark.parametrize('T', [28, 40, 54, 59])
+def test_sweepq_wide_kernels_vs_oracle(fb, orc, T):
+    """ kernels wider than the 27 the first-generation tensor-memory kernel stopped at (S2 at resolution 64 has T = 54):
+    the q kernels keep them on chip with four warps per CTA; against the oracle, bit for bit """
+    n = 4
+    s = sqrt(((2 * T + 1.5) ** 2 - 1) * n / 12.0)          # sigma / step that gives this half kernel size
+    assert fb.get_half_kernel_size_opt(s, 1.0, n) == T
+    rng = np.random.default_rng(T)
+    size = (2 * T + 40, 2 * T + 61)
+    pts = rng.uniform(0, 1, (3000, 2)) * (np.asarray(size) - 1)
+    pts[:100] = pts[100:200]
+    val = rng.normal(1000, 10, 3000)
+    a = fb.barnes(pts, val, s, [0.0, 0.0], 1.0, size, num_iter=n)
+    ref = orc.barnes(pts, val, s, [0.0, 0.0], 1.0, size, num_iter=n, nthreads=8)
+    assert bits_equal(a, ref)
+
+
+def test_spare_buffers_after_interleaved_x_sweep(fb, orc):
+    """ An x sweep that reads interleaved (value, weight) nodes followed by sweeps that are NOT in place -- a kernel so
+    wide that a launch takes one pass (2D), a 3D y sweep split into several launches: the later launches must write
+    planes into the free buffer pair, not into the interleaved alias the x sweep read (advisor finding, round 1). """
+    torch = pytest.importorskip('torch')
+    rng = np.random.default_rng(222)
+    # 2D: T_y = 449 -> one pass per launch on y (ping-pong between the buffer pairs); 24 fields x 57 line groups feed the
+    # tensor-memory x sweep that reads interleaved nodes
+    size, nf, N = (48, 912), 24, 600
+    step = 1.0
+    sig = [8.0, 520.0]
+    pts = rng.uniform(0, 1, (nf, N, 2)) * (np.asarray(size) - 1)
+    val = rng.normal(5, 2, (nf, N))
+    plan = fb.BarnesDevice(2, sig, [0.0, 0.0], step, size, nfields=nf, nsamples=nf * N, num_iter=4)
+    out = plan(torch.from_numpy(pts.reshape(nf * N, 2)).cuda(), torch.from_numpy(val.reshape(nf * N)).cuda()).cpu().numpy()
+    for i in (0, nf - 1):
+        ref = orc.barnes(pts[i], val[i], sig, [0.0, 0.0], step, size, num_iter=4, nthreads=8)
+        assert bits_equal(out[i], ref), i
+    # 3D: T_y = 222 with three passes -> the y sweep runs as 2 + 1 passes, the second launch is not in place
+    size3 = (40, 460, 44)                              # 44 planes x 29 line groups >= 1184 work items: interleaved x sweep
+    sig3 = [6.0, 223.0, 5.0]
+    n3 = 3
+    assert fb.get_half_kernel_size_opt(sig3[1], 1.0, n3) >= 222
+    pts3 = rng.uniform(0, 1, (2000, 3)) * (np.asarray(size3) - 1)
+    val3 = rng.normal(5, 2, 2000)
+    a = fb.barnes(pts3, val3, sig3, [0.0, 0.0, 0.0], step, size3, num_iter=n3)
+    ref = orc.barnes(pts3, val3, sig3, [0.0, 0.0, 0.0], step, size3, num_iter=n3, nthreads=8)
+    assert bits_equal(a, ref)
