@@ -9,7 +9,8 @@ shape: 2400x1200, step 1/32, sigma 1.0, N=50 000 samples per field).
 
 One process per GPU (torchrun sets RANK/LOCAL_RANK/WORLD_SIZE for N>1).  A step = one pass of
 the hot path (centre -> inject -> x sweep -> y sweep + mask/divide/cast) over a batch of F fields
-per GPU.  `value` is measured with the samples resident in HBM (CUDA events, max over ranks);
+per GPU (default 1024), run as sub-batches of 64 fields (one workspace of 5.9 GB fp64 state each)
+that rotate over four distinct sample sets.  `value` is measured with the samples resident in HBM (CUDA events, max over ranks);
 `e2e` goes through the HOST-buffer C-ABI call (pinned host memory; H2D of the samples and D2H
 of the float32 fields inside the timed region).  Per-kernel times for the roofline come from
 CUDA events recorded by the library on the launching stream during the same timed steps.
@@ -45,6 +46,8 @@ BYTES_ZERO = 16      # zero-fill of vg, wg
 BYTES_SWEEP_X = 32   # non-final fused sweep: 2 x 8 B read + 2 x 8 B write
 BYTES_SWEEP_Y = 20   # final fused sweep: 2 x 8 B read + 4 B float32 write
 BYTES_TOTAL_2D = 68
+SUB_FIELDS = 64      # fields per sub-batch (one call of the device-resident plan / of fb_barnes_host)
+N_SETS = 4           # distinct sample sets the sub-batches rotate over
 
 
 _JSON_OUT = None   # set by main(): duplicate of the original stdout
@@ -61,13 +64,15 @@ def make_fields(first_field, nfields):
 
 
 def config_dict(fields_per_gpu, n_gpus):
+    sub = min(SUB_FIELDS, fields_per_gpu)
     return {'workload': '2D optimized_convolution, %dx%d grid, step 1/32, sigma 1.0, num_iter 4, batched fields, '
                         'N=%d samples/field (BASELINE configs[4] shape; configs[0] grid)' % (SIZE[0], SIZE[1], N_PER_FIELD),
             'fields_per_gpu_per_step': fields_per_gpu, 'fields_per_step': fields_per_gpu * n_gpus,
             'grid': list(SIZE), 'samples_per_field': N_PER_FIELD, 'parallelism': 'fields sharded, no collective',
-            'cache': 'working set per step (%.1f GB fp64 state) exceeds L2; no flush needed'
-                     % (fields_per_gpu * POINTS_PER_FIELD * 32 / 1e9),
-            'streams': 'device-resident arm: consecutive batches alternate over 2 CUDA streams (own workspace each)'}
+            'sub_batch_fields': sub, 'sample_sets': N_SETS,
+            'cache': 'working set per sub-batch (%.1f GB fp64 state) exceeds L2; no flush needed'
+                     % (sub * POINTS_PER_FIELD * 32 / 1e9),
+            'streams': 'device-resident arm: consecutive sub-batches alternate over 2 CUDA streams (own workspace each)'}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -82,7 +87,7 @@ def cpu_fields_per_second(nfields, nthreads, repeats=1):
     def one(i):
         return orc.barnes(pts[i], val[i], SIGMA, X0, STEP, SIZE, num_iter=NUM_ITER, nthreads=1)
 
-    one(0)   # warm-up (page faults, library load)
+    ref0 = one(0)   # warm-up (page faults, library load); also the parity reference of bench.py
     best = None
     with ThreadPoolExecutor(max_workers=nthreads) as ex:
         for _ in range(repeats):
@@ -90,14 +95,14 @@ def cpu_fields_per_second(nfields, nthreads, repeats=1):
             list(ex.map(one, range(nfields)))
             dt = time.perf_counter() - t0
             best = dt if best is None or dt < best else best
-    return nfields / best, best
+    return nfields / best, best, ref0
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    nfields = max(cores, 8)
+    nfields = max(cores, 8)            # bounded sample of the step's fields: one per host thread
     from oracle import oracle as orc
     from concurrent.futures import ThreadPoolExecutor
     pts, val = make_fields(0, nfields)
@@ -116,11 +121,12 @@ def run_reference(args, rank, world):
                 times.append(dt)
     total = sum(times)
     value = nfields * POINTS_PER_FIELD * len(times) / total
-    sample = '%d fields per step (one per host thread) of the same 2400x1200 / N=50000 workload' % nfields
+    sample = ('%d fields per step (one per host thread) out of the %d fields of a step of the same 2400x1200 / N=50000 '
+              'workload' % (nfields, args.fields * args.gpus))
     line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * total / len(times),
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': config_dict(nfields, 1),
+            'config': config_dict(args.fields, args.gpus),
             'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
             'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
@@ -131,58 +137,87 @@ def run_reference(args, rank, world):
 # clocks
 
 class ClockSampler:
+    """ SM clock and throttle reasons of one GPU during the timed region: NVML polled every 10 ms from a thread
+    (pynvml), nvidia-smi -lms as the fallback. """
     QUERY = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
              'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
              'clocks_event_reasons.sw_power_cap')
 
     def __init__(self, gpu_index):
-        self.rows = []
+        self.rows = []          # (time, sm_mhz, set of reasons)
         self.proc = None
+        self.nvml = None
+        self.smmax = None
         self.gpu_index = gpu_index
+        self.stop_flag = False
 
     def start(self):
         try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self.gpu_index)
+            self.smmax = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu_index), '--query-gpu=' + self.QUERY,
-                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                          '--format=csv,noheader,nounits', '-lms', '20'],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        names = ((n.nvmlClocksThrottleReasonHwSlowdown, 'hw_slowdown'),
+                 (n.nvmlClocksThrottleReasonHwThermalSlowdown, 'hw_thermal_slowdown'),
+                 (n.nvmlClocksThrottleReasonSwThermalSlowdown, 'sw_thermal_slowdown'),
+                 (n.nvmlClocksThrottleReasonSwPowerCap, 'sw_power_cap'))
+        while not self.stop_flag:
+            try:
+                clk = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                mask = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                self.rows.append((time.perf_counter(), clk, {name for bit, name in names if mask & bit}))
+            except Exception:
+                pass
+            time.sleep(0.01)
+
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append((time.perf_counter(), line.strip()))
-
-    def stop(self, t_begin, t_end):
-        if self.proc is None:
-            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, smmax, reasons = [], None, set()
-        for (t, row) in self.rows:
-            f = [x.strip() for x in row.split(',')]
+            f = [x.strip() for x in line.strip().split(',')]
             if len(f) < 9:
                 continue
             try:
                 clk = float(f[1])
-                smmax = float(f[2])
+                self.smmax = float(f[2])
             except ValueError:
                 continue
-            if t_begin - 0.05 <= t <= t_end + 0.05:
-                sm.append(clk)
-                for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[5:9]):
-                    if v.lower().startswith('active'):
-                        reasons.add(name)
-        if not sm:   # timed region shorter than the sampling period: fall back to all samples
-            for (t, row) in self.rows:
-                f = [x.strip() for x in row.split(',')]
-                try:
-                    sm.append(float(f[1]))
-                except (ValueError, IndexError):
-                    pass
-        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': smmax, 'reasons': sorted(reasons),
-                'samples': len(sm)}
+            reasons = {name for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[5:9])
+                       if v.lower().startswith('active')}
+            self.rows.append((time.perf_counter(), clk, reasons))
+
+    def stop(self, t_begin, t_end):
+        if self.nvml is None and self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['no NVML / nvidia-smi']}
+        time.sleep(0.05)
+        self.stop_flag = True
+        if self.proc is not None:
+            self.proc.terminate()
+        inside = [(c, r) for (t, c, r) in self.rows if t_begin <= t <= t_end]
+        if not inside:   # timed region shorter than the sampling period: fall back to all samples
+            inside = [(c, r) for (t, c, r) in self.rows]
+        reasons = set()
+        for _, r in inside:
+            reasons |= r
+        sm = [c for c, _ in inside]
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_min_mhz': float(min(sm)) if sm else None,
+                'sm_max_mhz': self.smmax, 'reasons': sorted(reasons), 'samples': len(sm),
+                'source': 'NVML polled every 10 ms' if self.nvml is not None else 'nvidia-smi -lms'}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -212,6 +247,60 @@ def bind_to_gpu_numa_node(torch, local_rank):
     return None
 
 
+def extra_blocks(torch, fbi, L, dev):
+    """ Secondary measurements on one GPU: the literal paper case (BASELINE configs[0]: ONE 2400x1200 field, N=3490,
+    device-resident) and the S2 path at resolution 64 (BASELINE configs[3]: part 1 = projection + convolution on the
+    4096x2816 Lambert grid, part 2 = resampling to 4800x2400; host API, copies included) """
+    from math import exp
+    from fastbarnes import interpolationS2 as fbs2
+    out = {}
+    try:
+        g = np.load(os.path.join(ROOT, 'tests', 'golden', 'c1_paper.npz'))
+        pts, val = np.ascontiguousarray(g['pts'], dtype=np.float64), np.ascontiguousarray(g['val'], dtype=np.float64)
+    except Exception:
+        rng = np.random.default_rng(7)
+        pts = X0 + rng.uniform(0, 1, (3490, 2)) * np.asarray([(SIZE[0] - 1) / 32, (SIZE[1] - 1) / 32])
+        val = rng.normal(1000, 10, 3490)
+    n = len(val)
+    plan = fbi.BarnesDevice(2, SIGMA, X0, STEP, SIZE, nfields=1, nsamples=n, num_iter=NUM_ITER, device=dev)
+    d_p, d_v = torch.from_numpy(pts).to(dev), torch.from_numpy(val).to(dev)
+    for _ in range(5):
+        plan(d_p, d_v)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 50
+    e0.record()
+    for _ in range(reps):
+        plan(d_p, d_v)
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) * 1e3 / reps
+    out['c1_single_field'] = {'workload': 'ONE 2400x1200 field, N=%d, num_iter 4, device-resident (46 MB of fp64 state: L2 resident, '
+                                          'launch / latency bound)' % n,
+                              'us_per_field': us, 'value': POINTS_PER_FIELD / (us * 1e-6), 'unit': UNIT}
+    # S2, resolution 64 (demo/timing5_table5.py:100-102, :131-152 times the two parts separately)
+    step = 1.0 / 64
+    x0 = np.asarray([-26.0 + step, 34.5])
+    size = (4800, 2400)
+    mdw = exp(-3.5 ** 2 / 2)
+    sig = np.full(2, 1.0)
+    stp = np.full(2, step)
+    best1 = best2 = None
+    for _ in range(3):
+        t0 = time.perf_counter()
+        res1 = fbs2.interpolate_opt_convol_S2_part1(pts, val, sig, x0, stp, size, NUM_ITER, mdw)
+        t1 = time.perf_counter()
+        fbs2.interpolate_opt_convol_S2_part2(*res1)
+        t2 = time.perf_counter()
+        best1 = t1 - t0 if best1 is None or t1 - t0 < best1 else best1
+        best2 = t2 - t1 if best2 is None or t2 - t1 < best2 else best2
+    out['c4_s2'] = {'workload': 'barnes_S2 optimized_convolution_S2, N=%d, 4800x2400 lon/lat grid at 1/64 degree (Lambert grid '
+                                '4096x2816, T=54), host API with copies' % n,
+                    'ms_part1_projection_and_convolution': best1 * 1e3, 'ms_part2_resampling': best2 * 1e3,
+                    'reference_numba_seconds': {'part1': 1.200, 'part2': 0.381, 'source': 'SURVEY.md section 6.2 (build container, 1 thread)'}}
+    return out
+
+
 def run_gpu(args, rank, local_rank, world):
     import torch
     import torch.distributed as dist
@@ -228,28 +317,32 @@ def run_gpu(args, rank, local_rank, world):
     L = _lib.lib()
 
     # ---- device-resident arm ---------------------------------------------------------------------
-    pts_h, val_h = make_fields(rank * F, F)
-    pin_pts = torch.from_numpy(pts_h.reshape(F * N_PER_FIELD, 2)).pin_memory()
-    pin_val = torch.from_numpy(val_h.reshape(F * N_PER_FIELD)).pin_memory()
-    d_pts = pin_pts.to(dev, non_blocking=True)
-    d_val = pin_val.to(dev, non_blocking=True)
-    # one plan (workspace + output buffer) per stream: consecutive batches alternate between the
-    # streams so that the zero-fill / injection of batch i+1 overlaps the sweeps of batch i
+    SUB = min(SUB_FIELDS, F)
+    nsub = (F + SUB - 1) // SUB                      # sub-batches per step
+    F = nsub * SUB
+    # N_SETS distinct sample sets of SUB fields each (field seeds 2000 + rank * N_SETS * SUB + ...); the sub-batches
+    # of a step rotate over them, so consecutive launches never see the same samples
+    sets_h = [make_fields((rank * N_SETS + k) * SUB, SUB) for k in range(N_SETS)]
+    pin = [(torch.from_numpy(p_.reshape(SUB * N_PER_FIELD, 2)).pin_memory(),
+            torch.from_numpy(v_.reshape(SUB * N_PER_FIELD)).pin_memory()) for (p_, v_) in sets_h]
+    d_sets = [(a.to(dev, non_blocking=True), b.to(dev, non_blocking=True)) for (a, b) in pin]
+    # one plan (workspace + output buffer) per stream: consecutive sub-batches alternate between the
+    # streams so that the zero-fill / injection of sub-batch i+1 overlaps the sweeps of sub-batch i
     nstreams = max(1, args.streams)
-    plans = [fbi.BarnesDevice(2, SIGMA, X0, STEP, SIZE, nfields=F, nsamples=F * N_PER_FIELD, num_iter=NUM_ITER, device=dev)
+    plans = [fbi.BarnesDevice(2, SIGMA, X0, STEP, SIZE, nfields=SUB, nsamples=SUB * N_PER_FIELD, num_iter=NUM_ITER, device=dev)
              for _ in range(nstreams)]
     streams = [torch.cuda.Stream(device=dev) for _ in range(nstreams)]
     plan = plans[0]
     torch.cuda.synchronize()
 
     def run_steps(n):
-        """ n batches, round-robin over the streams; returns after enqueueing (caller synchronises) """
+        """ n steps = n * nsub sub-batches, round-robin over the streams and the sample sets; returns after enqueueing """
         cur = torch.cuda.current_stream()
         for s_ in streams:
             s_.wait_stream(cur)
-        for i in range(n):
+        for i in range(n * nsub):
             with torch.cuda.stream(streams[i % nstreams]):
-                plans[i % nstreams](d_pts, d_val)
+                plans[i % nstreams](*d_sets[i % N_SETS])
         for s_ in streams:
             cur.wait_stream(s_)
 
@@ -280,24 +373,27 @@ def run_gpu(args, rank, local_rank, world):
     t_end = time.perf_counter()
     ms_total = ev0.elapsed_time(ev1)
     launches = L.fb_kernel_launch_count() - launches0
-    # per-kernel durations: re-run the timed count with the library's per-stage events read back
-    # after every step (reading them forces a sync, so this is a separate loop from `value`)
-    for _ in range(args.steps):
-        plan(d_pts, d_val)
+    clocks = sampler.stop(t_begin, t_end)
+    # per-kernel durations: the library's per-stage CUDA events (recorded on the launching stream) of single
+    # sub-batches, read back after every call (reading forces a sync, so this is a separate loop from `value`)
+    nprof = max(args.steps, 8)
+    for i in range(nprof):
+        plan(*d_sets[i % N_SETS])
         _lib.check(L.fb_last_profile(seg.ctypes.data_as(_lib.c_double_p), 5, nl.ctypes.data_as(_lib.c_i64_p)))
         seg_ms += seg
-    seg_ms /= args.steps
+    seg_ms /= nprof
     L.fb_set_profiling(0)
-    clocks = sampler.stop(t_begin, t_end)
+    # field 0 of sample set 0 as the timed arm computes it (checked against the oracle below)
+    check_dev = plan(*d_sets[0])[0].cpu().numpy() if rank == 0 else None
 
     # ---- secondary: the same batches in fp32 working precision (north_star's fp32 path; not the headline,
     # the reference computes in fp64) ----------------------------------------------------------------
     fp32 = None
     if not args.no_fp32:
-        plans32 = [fbi.BarnesDevice(2, SIGMA, X0, STEP, SIZE, nfields=F, nsamples=F * N_PER_FIELD, num_iter=NUM_ITER,
+        plans32 = [fbi.BarnesDevice(2, SIGMA, X0, STEP, SIZE, nfields=SUB, nsamples=SUB * N_PER_FIELD, num_iter=NUM_ITER,
                                     device=dev, precision='fp32') for _ in range(nstreams)]
         plans64, plans[:] = list(plans), plans32
-        run_steps(args.warmup)
+        run_steps(min(args.warmup, 2))
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -307,31 +403,41 @@ def run_gpu(args, rank, local_rank, world):
         ms32 = e0.elapsed_time(e1)
         L.fb_set_profiling(1)
         seg32 = np.zeros(5)
-        for _ in range(args.steps):
-            plans32[0](d_pts, d_val)
+        for i in range(nprof):
+            plans32[0](*d_sets[i % N_SETS])
             _lib.check(L.fb_last_profile(seg.ctypes.data_as(_lib.c_double_p), 5, nl.ctypes.data_as(_lib.c_i64_p)))
             seg32 += seg
-        seg32 /= args.steps
+        seg32 /= nprof
         L.fb_set_profiling(0)
         plans[:] = plans64
         fp32 = (ms32, seg32)
         del plans32
 
+    # ---- secondary blocks (rank 0, single GPU): the literal paper field and the S2 path -----------------
+    extra = {}
+    if rank == 0 and world == 1 and not args.no_extra:
+        extra = extra_blocks(torch, fbi, L, dev)
+
     # ---- end-to-end arm: host buffers through the C ABI -----------------------------------------------
-    out_pin = torch.empty((F,) + SIZE[::-1], dtype=torch.float32).pin_memory()
+    out_pin = torch.empty((SUB,) + SIZE[::-1], dtype=torch.float32).pin_memory()
     prob = plan.prob
-    h2d = pin_pts.numel() * 8 + pin_val.numel() * 8
-    d2h = out_pin.numel() * 4
+    h2d = nsub * (pin[0][0].numel() * 8 + pin[0][1].numel() * 8)
+    d2h = nsub * out_pin.numel() * 4
+    e2e_calls = [0]
 
     def e2e_step():
-        _lib.check(L.fb_barnes_host(prob, F * N_PER_FIELD, None, pin_pts.data_ptr(), pin_val.data_ptr(),
-                                    out_pin.data_ptr(), None))
+        for _ in range(nsub):
+            k = e2e_calls[0] % N_SETS
+            e2e_calls[0] += 1
+            _lib.check(L.fb_barnes_host(prob, SUB * N_PER_FIELD, None, pin[k][0].data_ptr(), pin[k][1].data_ptr(),
+                                        out_pin.data_ptr(), None))
 
-    for _ in range(max(1, min(args.warmup, 3))):
-        e2e_step()
+    _lib.check(L.fb_barnes_host(prob, SUB * N_PER_FIELD, None, pin[0][0].data_ptr(), pin[0][1].data_ptr(), out_pin.data_ptr(), None))
+    check_e2e = out_pin[0].numpy().copy() if rank == 0 else None
+    e2e_step()
     barrier()
     t0 = time.perf_counter()
-    e2e_steps = max(1, min(args.steps, 10))
+    e2e_steps = max(1, min(args.steps, 5))
     for _ in range(e2e_steps):
         e2e_step()
     barrier()
@@ -354,7 +460,7 @@ def run_gpu(args, rank, local_rank, world):
             pass
         peak = float(peaks.get('hbm_gbs', 6650.0))
         peak_src = 'measured (MEASURED_PEAKS.json)' if 'hbm_gbs' in peaks else 'fallback (B200_PROFILING.md)'
-        pts_launch = F * POINTS_PER_FIELD
+        pts_launch = SUB * POINTS_PER_FIELD              # one launch of a sweep kernel = one sub-batch
         gx = BYTES_SWEEP_X * pts_launch / (seg_ms[2] * 1e-3) / 1e9 if seg_ms[2] > 0 else 0.0
         gy = BYTES_SWEEP_Y * pts_launch / (seg_ms[3] * 1e-3) / 1e9 if seg_ms[3] > 0 else 0.0
         dominant_is_x = seg_ms[2] >= seg_ms[3]
@@ -376,19 +482,20 @@ def run_gpu(args, rank, local_rank, world):
             'gpu_launches': int(launches),
             'roofline': {
                 'bound': 'hbm',
-                'kernel': 'fb_sweeph_kernel<2,2,1,8,2> (x sweep: 4 fused passes, two-warp pipelines, rings in tensor memory, interleaved (value, weight) input, transposing output)' if dominant_is_x
-                          else 'fb_sweeph_kernel<2,2,2,8,1> (y sweep: 4 fused passes + mask/divide/cast, two-warp pipelines, rings in tensor memory)',
+                'kernel': 'fb_sweepq_kernel<4,1,1> (x sweep: 4 fused passes per warp, TMA row staging, rings in tensor + shared memory, TMA transposing store)' if dominant_is_x
+                          else 'fb_sweepq_kernel<4,1,2> (y sweep: 4 fused passes per warp + mask/divide/cast, TMA row staging, rings in tensor + shared memory)',
                 'achieved': gx if dominant_is_x else gy, 'peak': peak, 'unit': 'GB/s',
                 'frac': (gx if dominant_is_x else gy) / peak, 'traffic': traffic, 'peak_source': peak_src,
                 'algorithmic_bytes_per_point': BYTES_SWEEP_X if dominant_is_x else BYTES_SWEEP_Y,
                 'points_per_launch': pts_launch,
                 'ms_per_launch': float(seg_ms[2] if dominant_is_x else seg_ms[3]),
-                'other_kernels': {'sweep_x_GBps': gx, 'sweep_y_GBps': gy, 'ms_zero_fill': float(seg_ms[0]),
+                'other_kernels': {'sweep_x_GBps': gx, 'sweep_y_GBps': gy, 'sweep_x_frac': gx / peak, 'sweep_y_frac': gy / peak,
+                                  'ms_zero_fill': float(seg_ms[0]),
                                   'ms_minmax_inject': float(seg_ms[1]), 'ms_sweep_x': float(seg_ms[2]),
                                   'ms_sweep_y': float(seg_ms[3])},
                 'whole_step': {'algorithmic_bytes_per_point': BYTES_TOTAL_2D,
-                               'achieved_GBps': BYTES_TOTAL_2D * pts_launch * args.steps / (ms_total * 1e-3) / 1e9 / 1.0,
-                               'frac_of_peak': BYTES_TOTAL_2D * pts_launch * args.steps / (ms_total * 1e-3) / 1e9 / peak},
+                               'achieved_GBps': BYTES_TOTAL_2D * F * POINTS_PER_FIELD * args.steps / (ms_total * 1e-3) / 1e9,
+                               'frac_of_peak': BYTES_TOTAL_2D * F * POINTS_PER_FIELD * args.steps / (ms_total * 1e-3) / 1e9 / peak},
             },
             'clocks': clocks,
         }
@@ -404,13 +511,30 @@ def run_gpu(args, rank, local_rank, world):
                 'sweep_y_GBps': by * pts_launch / (s32[3] * 1e-3) / 1e9 if s32[3] > 0 else 0.0,
                 'sweep_x_frac_of_peak': bx * pts_launch / (s32[2] * 1e-3) / 1e9 / peak if s32[2] > 0 else 0.0,
                 'sweep_y_frac_of_peak': by * pts_launch / (s32[3] * 1e-3) / 1e9 / peak if s32[3] > 0 else 0.0}
+        line.update(extra)
         if world == 1 and not args.no_cpu:
             cores = os.cpu_count() or 1
             nf = max(cores, 8) * 6          # about 20 core-seconds of CPU work
-            fps, secs = cpu_fields_per_second(nf, cores)
+            fps, secs, ref0 = cpu_fields_per_second(nf, cores)
             line['cpu_baseline'] = {'value': fps * POINTS_PER_FIELD, 'unit': UNIT, 'cores': cores, 'kind': 'port',
                                     'sample': '%d fields of the same workload, one field per host thread, %.1f s wall'
                                               % (nf, secs)}
+            try:
+                with open(os.path.join(ROOT, 'profiles', 'r2_numba_reference_cpu.json')) as f:
+                    nj = json.load(f)
+                line['cpu_baseline']['numba_reference_single_thread'] = {
+                    'value': nj['cases']['c5_field_N50000']['grid_points_per_s'], 'unit': UNIT, 'where': nj['where'],
+                    'note': 'the unmodified reference under Numba, 1 thread, measured in the build container (its sources '
+                            'are not in this repository); orientation only'}
+            except Exception:
+                pass
+            # the oracle computed field 0 of sample set 0 (seed 2000) a moment ago: the timed arm and the end-to-end arm
+            # must reproduce it bit for bit
+            same_dev = bool(np.array_equal(check_dev.view(np.uint32), ref0.view(np.uint32)))
+            same_e2e = bool(np.array_equal(check_e2e.view(np.uint32), ref0.view(np.uint32)))
+            line['parity_checked'] = same_dev and same_e2e
+            line['parity'] = {'field': 'seed 2000 (field 0 of sample set 0)', 'device_resident_arm_bit_identical': same_dev,
+                              'e2e_arm_bit_identical': same_e2e, 'against': 'oracle port (oracle/fb_oracle.c), float32 field'}
         print(json.dumps(line), file=_JSON_OUT or sys.stdout, flush=True)
     if world > 1:
         dist.barrier()
@@ -422,7 +546,8 @@ def main():
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
-    ap.add_argument('--fields', type=int, default=64, help='fields per GPU per step')
+    ap.add_argument('--fields', type=int, default=1024, help='fields per GPU per step (run as sub-batches of 64)')
+    ap.add_argument('--no-extra', action='store_true', help='skip the single-field and S2 blocks')
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--streams', type=int, default=2, help='device-resident arm: batches alternate over this many streams')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')

@@ -1401,7 +1401,7 @@ namespace {
 constexpr int kHostStreams = 3;
 cudaStream_t g_host_streams[kHostStreams] = {nullptr, nullptr, nullptr};
 int g_host_streams_device = -1;
-std::atomic<int> g_host_chunk_fields{4};
+std::atomic<int> g_host_chunk_fields{16};   // 16 x 75 line groups >= 8 per SM: the chunks run the q / tensor-memory kernels
 
 int host_streams_get()
 {
