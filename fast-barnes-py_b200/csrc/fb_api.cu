@@ -41,6 +41,8 @@ std::atomic<int> g_sweepq{1};
 std::atomic<int> g_q_nst{3};        // staging slots (chunks of rows in flight) per warp
 std::atomic<int> g_q_pf{0};         // extra chunks of lead of the L2 prefetch (0: none)
 std::atomic<int> g_q_warps{8};      // warps per CTA the plan starts with (8 or 4)
+// q path: injection as sort by cell + segmented reduce feeding the x sweep (fb_sparse.cuh) instead of dense grids
+std::atomic<int> g_sparse{0};       // opt-in: measured slower than the dense path (x sweep 1.55 vs 1.15 ms on the bench batch), see DESIGN.md
 
 int fail(int code, const char *fmt, ...)
 {
@@ -442,7 +444,7 @@ inline size_t sweepq_smem_bytes(int mode, int warps, int smem_per_warp)
     return (mode == 2 ? 0 : (size_t)warps * FBQ_TILE_BYTES) + (size_t)warps * smem_per_warp;
 }
 
-SweepQPlan sweepq_plan(int npass, int mode, int D)
+SweepQPlan sweepq_plan(int npass, int mode, int D, int header = 128, int extra_per_warp = 0, int nst_force = 0)
 {
     SweepQPlan q{};
     q.ok = false;
@@ -453,16 +455,17 @@ SweepQPlan sweepq_plan(int npass, int mode, int D)
     int nst_want = g_q_nst.load();
     if (nst_want < 2) nst_want = 2;
     if (nst_want > FBQ_MAX_STAGES) nst_want = FBQ_MAX_STAGES;
-    for (int warps = (g_q_warps.load() >= 8 ? 8 : 4); warps >= 4; warps -= 4) {
+    if (nst_force > 0) nst_want = nst_force;
+    for (int warps = ((g_q_warps.load() >= 8 || nst_force > 0) ? 8 : 4); warps >= (nst_force > 0 ? 8 : 4); warps -= 4) {
         const int cols = warps == 8 ? 256 : 512;
         int nt = cols / (2 * q.RP);
         if (nt > nr) nt = nr;
         const int ns = nr - nt;
         if (ns > 1) continue;
         for (int nst = nst_want; nst >= 2; --nst) {
-            const size_t off_ring = 128 + (size_t)nst * FBQ_STAGE_BYTES;
+            const size_t off_ring = (size_t)header + (size_t)nst * FBQ_STAGE_BYTES;
             const size_t per = off_ring + (size_t)ns * q.RP * 256;
-            if (sweepq_smem_bytes(mode, warps, (int)per) > kQSmemLimit) continue;
+            if (sweepq_smem_bytes(mode, warps, (int)per) + (size_t)warps * extra_per_warp > kQSmemLimit) continue;
             q.ok = true;
             q.warps = warps; q.ns = ns; q.nst = nst; q.cols_per_warp = cols;
             q.smem_per_warp = (int)per; q.off_ring = (int)off_ring;
@@ -588,6 +591,89 @@ int launch_sweepq_m(int npass, const FbSweepQ &p, const SweepQPlan &q, cudaStrea
     case 51: return launch_sweepq_t<5, 1, MODE>(p, q, st);
     case 60: return launch_sweepq_t<6, 0, MODE>(p, q, st);
     case 61: return launch_sweepq_t<6, 1, MODE>(p, q, st);
+    }
+    return fail(FB_EINVAL, "unsupported q-sweep configuration: %d passes, %d shared-memory rings", npass, q.ns);
+#endif
+}
+
+// ---- the x sweep fed by the binned samples (fb_sweepqs_kernel) -----------------------------------------------------
+// geometry of the binning: it must agree with the stream of the x sweep (chunks of 8 rows starting at t_begin)
+FbBins bins_geometry(int num_iter, int T, long long W, long long H, long long n_outer)
+{
+    FbBins bn{};
+    const int lag = num_iter * (T + 1);
+    bn.t_begin = -((FBQ_U - lag % FBQ_U) % FBQ_U);
+    bn.G = (int)((H + 15) / 16);
+    bn.NB = ((int)((W - 1 - bn.t_begin) / FBQ_U) + 1 + 3) / 4 * 4;       // multiple of 4: the rows of bin_start stay 16-byte aligned
+
+    bn.nbuckets = n_outer * bn.G * bn.NB;
+    return bn;
+}
+
+// a pass warp's share of the producer area: 64 B of mbarriers, the bucket table of a line group, the prefetch slots
+inline int sweepqs_prod_bytes(int nb) { return 64 + (int)(((size_t)(nb + 1) * 4 + 127) / 128 * 128) + FBQS_PF * (int)FBQS_PF_BYTES; }
+
+template <int NPASS, int NS>
+int launch_sweepqs_t(FbSweepQ p, const SweepQPlan &q, cudaStream_t st)
+{
+    static thread_local bool configured[16] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!configured[dev & 15]) {
+        CUDA_TRY(cudaFuncSetAttribute(fb_sweepqs_kernel<NPASS, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kQSmemLimit));
+        CUDA_TRY(cudaFuncSetAttribute(fb_sweepqs_kernel<NPASS, NS>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                      cudaSharedmemCarveoutMaxShared));
+        configured[dev & 15] = true;
+    }
+    const long long nitems = p.n_outer * p.n_groups;
+    if (nitems <= 0) return FB_OK;
+    CUtensorMap tm_out;
+    const unsigned long long orow = (unsigned long long)p.L * 16ull;
+    int rc = make_tensor_map(tm_out, p.out, 2ull * p.L, (unsigned long long)p.n_inner, (unsigned long long)p.n_outer, orow,
+                             orow * p.n_inner, 16, 16, true, false);
+    if (rc != FB_OK) return rc;
+    const int sms = sm_count(dev);
+    const int warps = 8;                                 // two warpgroups of pass warps + two of producer warps
+    if (q.warps != 8 || q.nst != 2) return fail(FB_EKERNEL, "internal: plan of the sparse x sweep");
+    long long grid = (nitems + warps - 1) / warps;
+    if (grid > sms) grid = sms;
+    // producer area per pass warp: 64 B of mbarriers, the bucket table of a line group, the prefetch slots
+    p.prod_bytes = sweepqs_prod_bytes(p.nb);
+    const size_t smem = sweepq_smem_bytes(1, warps, q.smem_per_warp) + (size_t)warps * p.prod_bytes;
+    if (smem > kQSmemLimit) return fail(FB_EKERNEL, "internal: shared memory of the sparse x sweep (%zu bytes)", smem);
+    p.tmem_alloc_cols = 32;
+    if (warps > 4) p.tmem_alloc_cols = 512;
+    else
+        while (p.tmem_alloc_cols < (NPASS - 1 - NS) * 2 * q.RP) p.tmem_alloc_cols *= 2;
+    p.ncw = warps;
+    const int threads = 2 * warps * 32;
+    if (getenv("FB_DEBUG"))
+        fprintf(stderr, "[fb] sweepqs<%d,%d> warps %d+%d grid %lld smem %zu nst %d R %d RP %d D %d items %lld buckets/group %d\n", NPASS,
+                NS, warps, warps, grid, smem, q.nst, q.R, q.RP, p.D, nitems, p.nb);
+    CUDA_TRY(cudaMemsetAsync(p.work_counter, 0, sizeof(unsigned long long), st));
+    fb_sweepqs_kernel<NPASS, NS><<<(unsigned)grid, threads, smem, st>>>(p, tm_out);
+    LAUNCH_CHECK();
+    return FB_OK;
+}
+
+int launch_sweepqs(int npass, const FbSweepQ &p, const SweepQPlan &q, cudaStream_t st)
+{
+#ifdef FBQ_LAB
+    if (npass == 4 && q.ns == 1) return launch_sweepqs_t<4, 1>(p, q, st);
+    return fail(FB_EKERNEL, "lab build: kernel family compiled out");
+#else
+    switch (npass * 10 + q.ns) {
+    case 10: return launch_sweepqs_t<1, 0>(p, q, st);
+    case 20: return launch_sweepqs_t<2, 0>(p, q, st);
+    case 21: return launch_sweepqs_t<2, 1>(p, q, st);
+    case 30: return launch_sweepqs_t<3, 0>(p, q, st);
+    case 31: return launch_sweepqs_t<3, 1>(p, q, st);
+    case 40: return launch_sweepqs_t<4, 0>(p, q, st);
+    case 41: return launch_sweepqs_t<4, 1>(p, q, st);
+    case 50: return launch_sweepqs_t<5, 0>(p, q, st);
+    case 51: return launch_sweepqs_t<5, 1>(p, q, st);
+    case 60: return launch_sweepqs_t<6, 0>(p, q, st);
+    case 61: return launch_sweepqs_t<6, 1>(p, q, st);
     }
     return fail(FB_EINVAL, "unsupported q-sweep configuration: %d passes, %d shared-memory rings", npass, q.ns);
 #endif
@@ -951,6 +1037,9 @@ struct Workspace {
     unsigned int *seg_base, *seg_n;
     double *seg[4];          // 1D segmented path: extended segments (v, w) x (in, out)
     unsigned int *link_next; // two-pass injection: successor of every record in its node's list
+    FbRec *bin_rec;          // binned injection: the records (aliases rec_k .. seg_base, which the dense injection uses)
+    unsigned int *bin_cnt, *bin_start, *bin_sums;   // binned injection (fb_sparse.cuh): records per bucket, first record, scan scratch
+    long long bin_cap;       // buckets the bin arrays hold
     size_t bytes;
 };
 
@@ -969,7 +1058,8 @@ void carve(Workspace &w, char *base, const fb_problem *pr, long long total, long
     w.counters = (unsigned long long *)take((4 + kSweepCounterSlots) * 8);
     w.offsets = (long long *)take((size_t)(pr->nfields + 1) * 8);
     w.first_mask = (unsigned char *)take((size_t)nsamples + 1);
-    w.rec_k = (int *)take(R * 4 + 4);
+    w.rec_k = (int *)take(R * 4 + 4);                       // rec_k .. seg_base: 4 + 8 + 8 + 8 + 4 = 32 bytes per record, contiguous
+    w.bin_rec = (FbRec *)w.rec_k;
     w.rec_w = (double *)take(R * 8 + 8);
     w.rec_wv = (double *)take(R * 8 + 8);
     w.seg_node = (long long *)take(R * 8 + 8);
@@ -978,6 +1068,12 @@ void carve(Workspace &w, char *base, const fb_problem *pr, long long total, long
     for (int i = 0; i < 4; ++i)
         w.seg[i] = (sp && sp->on) ? (double *)take((size_t)sp->Le * sp->n_seg * sizeof(double)) : nullptr;
     w.link_next = (unsigned int *)take(R * 4 + 4);
+    // buckets of the binned injection: (field x z plane) x 16-line groups along y x chunks of 8 rows along x (+ 2 for the
+    // stream offset), dim >= 2 only
+    w.bin_cap = pr->dim >= 2 ? (long long)pr->nfields * (pr->dim > 2 ? pr->size[2] : 1) * ((pr->size[1] + 15) / 16) * (pr->size[0] / 8 + 6) : 0;
+    w.bin_cnt = (unsigned int *)take((size_t)(w.bin_cap + 1) * 4);
+    w.bin_start = (unsigned int *)take((size_t)(w.bin_cap + 8) * 4);       // + slack: the producers copy whole 16-byte units
+    w.bin_sums = (unsigned int *)take((size_t)(w.bin_cap / (FB_SCAN_BLOCK * FB_SCAN_PER_THREAD) + 4) * 4);
     w.bytes = off;
 }
 
@@ -1115,6 +1211,76 @@ bool use_sweepq(const fb_problem *pr, const Derived &d)
     return true;
 }
 
+// The q path can take its x-sweep input from the binned samples instead of a dense injected grid.
+bool use_sparse(const fb_problem *pr, const Derived &d, long long nsamples, long long max_n)
+{
+    if (g_sparse.load() == 0 || !use_sweepq(pr, d)) return false;
+    if (max_n >= FB_BIN_MAX_SAMPLES || (nsamples << pr->dim) >= 0xfffffff0LL) return false;      // record key / index bits
+    const FbBins bn = bins_geometry(pr->num_iter, d.ax[0].T, d.W, d.H, (long long)pr->nfields * d.Dz);
+    if (!sweepq_plan(pr->num_iter, 1, 2 * d.ax[0].T + 2, 256, sweepqs_prod_bytes(bn.NB), 2).ok) return false;
+    // the sparse x sweep runs with 8 pass + 8 producer warps per CTA (register redistribution between the warpgroups)
+    const long long items = (long long)pr->nfields * d.Dz * bn.G;
+    return items >= 8LL * sm_count_current() && bn.nbuckets < (1LL << 31) && d.W < (1LL << 27);
+}
+
+// min / max of the values, then sort by cell + segmented reduce (fb_sparse.cuh): no dense grid is touched
+int run_inject_sparse(const fb_problem *pr, const Derived &d, long long nsamples, const int64_t *h_offsets, const double *d_pts,
+                      const double *d_val, Workspace &w, cudaStream_t st)
+{
+    long long max_n = 0;
+    int rc = check_offsets(pr, nsamples, h_offsets, max_n);
+    if (rc != FB_OK) return rc;
+    const FbBins bn = bins_geometry(pr->num_iter, d.ax[0].T, d.W, d.H, (long long)pr->nfields * d.Dz);
+    if (bn.nbuckets > w.bin_cap) return fail(FB_EINVAL, "internal: bucket arrays too small (%lld > %lld)", bn.nbuckets, w.bin_cap);
+    CUDA_TRY(cudaMemsetAsync(w.bin_cnt, 0, (size_t)(bn.nbuckets + 1) * 4, st));
+    fb_init_kernel<<<(unsigned)((pr->nfields + 255) / 256), 256, 0, st>>>(w.mm, pr->nfields, w.counters);
+    LAUNCH_CHECK();
+    if ((rc = prof_mark(1, st)) != FB_OK) return rc;
+    FbSamples s{};
+    s.pts = d_pts;
+    s.val = d_val;
+    if (h_offsets) {
+        CUDA_TRY(cudaMemcpyAsync(w.offsets, h_offsets, (size_t)(pr->nfields + 1) * 8, cudaMemcpyHostToDevice, st));
+        s.offsets = w.offsets;
+        s.n_uniform = 0;
+    } else {
+        s.offsets = nullptr;
+        s.n_uniform = max_n;
+    }
+    const long long nscan = bn.nbuckets;
+    const int nblocks = (int)((nscan + FB_SCAN_BLOCK * FB_SCAN_PER_THREAD - 1) / (FB_SCAN_BLOCK * FB_SCAN_PER_THREAD));
+    if (max_n > 0) {
+        FbGrid gr{};
+        gr.dim = pr->dim;
+        gr.W = d.W; gr.H = d.H; gr.Dz = d.Dz; gr.total = d.total;
+        gr.z_off = 0; gr.z_cnt = d.Dz;
+        for (int m = 0; m < 3; ++m) { gr.x0[m] = pr->x0[m]; gr.step[m] = pr->step[m]; }
+        const unsigned nf = (unsigned)pr->nfields;
+        long long mmb = (max_n + 256 * 8 - 1) / (256 * 8);
+        if (mmb > 1024) mmb = 1024;
+        fb_minmax_kernel<<<dim3((unsigned)mmb, nf), 256, 0, st>>>(s, w.mm);
+        LAUNCH_CHECK();
+        const dim3 sg((unsigned)((max_n + 255) / 256), nf);
+        fb_bin_count_kernel<<<sg, 256, 0, st>>>(s, gr, bn, w.bin_cnt);
+        LAUNCH_CHECK();
+        fb_scan_local_kernel<<<(unsigned)nblocks, FB_SCAN_BLOCK, 0, st>>>(w.bin_cnt, w.bin_start, w.bin_sums, nscan);
+        LAUNCH_CHECK();
+        fb_scan_sums_kernel<<<1, 1024, 0, st>>>(w.bin_sums, nblocks, w.bin_sums + nblocks + 1);
+        LAUNCH_CHECK();
+        fb_scan_add_kernel<<<(unsigned)nblocks, FB_SCAN_BLOCK, 0, st>>>(w.bin_start, w.bin_sums, w.bin_sums + nblocks + 1, nscan);
+        LAUNCH_CHECK();
+        fb_bin_fill_kernel<<<sg, 256, 0, st>>>(s, gr, bn, w.mm, w.bin_start, w.bin_cnt, w.bin_rec);
+        LAUNCH_CHECK();
+        long long rb = (bn.nbuckets + 32 * FB_RED_WARPS - 1) / (32 * FB_RED_WARPS);
+        if (rb > 148 * 16) rb = 148 * 16;
+        fb_bin_reduce_kernel<<<(unsigned)rb, 32 * FB_RED_WARPS, 0, st>>>(bn, w.bin_start, w.bin_rec);
+        LAUNCH_CHECK();
+    } else {
+        CUDA_TRY(cudaMemsetAsync(w.bin_start, 0, (size_t)(bn.nbuckets + 1) * 4, st));    // no samples: every bucket is empty
+    }
+    return FB_OK;
+}
+
 bool inject_interleaved(const fb_problem *pr, const Derived &d)
 {
     if (use_sweepq(pr, d)) return true;
@@ -1123,7 +1289,7 @@ bool inject_interleaved(const fb_problem *pr, const Derived &d)
 }
 
 int run_sweeps(const fb_problem *pr, const Derived &d, Workspace &w, float *d_out, double *d_out64, cudaStream_t st,
-               const SegPlan &sp)
+               const SegPlan &sp, bool sparse = false)
 {
     const long long nf = pr->nfields;
     const int n = pr->num_iter;
@@ -1173,7 +1339,27 @@ int run_sweeps(const fb_problem *pr, const Derived &d, Workspace &w, float *d_ou
     if (use_sweepq(pr, d)) {
         // interleaved nodes throughout: A (injected, [..][x][y]) -> B (natural order) -> float32 field
         double *a2 = w.vA, *b2 = w.vB;                   // vB and wB are adjacent: one block of 2 g bytes
-        rc = run_sweepq(1, n, d.ax[0], a2, b2, nullptr, nullptr, w.mm, d.csf, nf * d.Dz, d.W, d.H, st, ctr);
+        if (sparse) {
+            // the x sweep synthesises its rows from the binned samples (run_inject_sparse)
+            const int D = 2 * d.ax[0].T + 2;
+            const FbBins bn = bins_geometry(n, d.ax[0].T, d.W, d.H, nf * d.Dz);
+            const SweepQPlan q = sweepq_plan(n, 1, D, 256, sweepqs_prod_bytes(bn.NB), 2);
+            FbSweepQ p{};
+            p.in = nullptr; p.out = b2; p.mm = w.mm;
+            p.n_outer = nf * d.Dz; p.L = d.W; p.n_inner = d.H; p.n_groups = (d.H + 15) / 16;
+            p.T = d.ax[0].T; p.D = D; p.R = q.R; p.RP = q.RP;
+            p.alpha = d.ax[0].alpha; p.csf = d.csf;
+            p.work_counter = ctr.base + (ctr.next++ % kSweepCounterSlots);
+            p.nst = q.nst; p.pf = 0;
+            p.tmem_cols_per_warp = q.cols_per_warp;
+            p.smem_per_warp = q.smem_per_warp; p.off_ring = q.off_ring;
+            p.nb = bn.NB;
+            p.bin_start = w.bin_start;
+            p.nodes = w.bin_rec;
+            rc = launch_sweepqs(n, p, q, st);
+        } else {
+            rc = run_sweepq(1, n, d.ax[0], a2, b2, nullptr, nullptr, w.mm, d.csf, nf * d.Dz, d.W, d.H, st, ctr);
+        }
         if (rc != FB_OK) return rc;
         if ((rc = prof_mark(3, st)) != FB_OK) return rc;
         if (pr->dim == 2) {
@@ -1244,11 +1430,17 @@ int pipeline(const fb_problem *pr, long long nsamples, const int64_t *h_offsets,
     g_prof.launches_begin = g_launches.load();
     g_prof.marked = 0;
     if ((rc = prof_mark(0, st)) != FB_OK) return rc;
-    rc = run_inject(pr, d, nsamples, h_offsets, d_pts, d_val, w, st, 0, -1, (pr->flags & FB_FLAG_FP32) != 0,
-                    inject_interleaved(pr, d));
+    long long max_n = 0;
+    if ((rc = check_offsets(pr, nsamples, h_offsets, max_n)) != FB_OK) return rc;
+    const bool sparse = use_sparse(pr, d, nsamples, max_n);
+    if (sparse)
+        rc = run_inject_sparse(pr, d, nsamples, h_offsets, d_pts, d_val, w, st);
+    else
+        rc = run_inject(pr, d, nsamples, h_offsets, d_pts, d_val, w, st, 0, -1, (pr->flags & FB_FLAG_FP32) != 0,
+                        inject_interleaved(pr, d));
     if (rc != FB_OK) return rc;
     if ((rc = prof_mark(2, st)) != FB_OK) return rc;
-    rc = run_sweeps(pr, d, w, d_out, d_out64, st, sp);
+    rc = run_sweeps(pr, d, w, d_out, d_out64, st, sp, sparse);
     if (rc != FB_OK) return rc;
     g_prof.launches_end = g_launches.load();
     g_prof.armed = g_profiling.load() != 0;
@@ -2162,6 +2354,7 @@ FB_EXPORT int fb_set_option(const char *name, int value)
     if (!strcmp(name, "sweepq_stages")) { g_q_nst.store(value); return FB_OK; }
     if (!strcmp(name, "sweepq_prefetch")) { g_q_pf.store(value); return FB_OK; }
     if (!strcmp(name, "sweepq_warps")) { g_q_warps.store(value); return FB_OK; }
+    if (!strcmp(name, "sparse_inject")) { g_sparse.store(value); return FB_OK; }
     return fail(FB_EINVAL, "unknown option: %s", name);
 }
 

@@ -33,6 +33,7 @@
 #pragma once
 #include "fb_kernels.cuh"
 #include <cuda.h>   // CUtensorMap (types only: the encoder is looked up at run time)
+#include "fb_sparse.cuh"
 
 #define FBQ_U 8                 // steps per chunk
 #define FBQ_STAGE_BYTES 4096    // one staging slot: 8 new rows + 8 old rows of 256 bytes (16 lines x 2 fields x 8 B)
@@ -58,6 +59,12 @@ struct FbSweepQ {
     int tmem_alloc_cols;         // columns the CTA allocates (power of two >= 32; 512 when more than 4 warps run)
     int smem_per_warp;           // bytes of a warp's block of dynamic shared memory: [mbarriers 128 B][stages][rings]
     int off_ring;                // byte offset of the rings inside that block (stages start at 128)
+    // fb_sweepqs_kernel (rows from the binned samples, fb_sparse.cuh)
+    int ncw;                     // pass warps per CTA (the producer warps follow them)
+    int nb;                      // buckets (chunks of 8 rows) per line group
+    const unsigned int *bin_start;   // [n_outer * n_groups * nb + 1] first entry of every bucket
+    int prod_bytes;                  // bytes of a pass warp's share of the producer area (mbarriers, bucket table, prefetch slots)
+    const FbRec *nodes;              // entries: key = (row << 4 | line in group) or FB_BIN_HOLE, w / wv = the node's sums
 };
 
 __device__ __forceinline__ unsigned fbq_smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -81,6 +88,21 @@ __device__ __forceinline__ void fbq_mbar_wait(unsigned bar, unsigned parity)
         "bra FBQ_WAIT;\n"
         "FBQ_DONE:\n"
         "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+// wait of a warp that has nothing else to do (a producer that is ahead of its pass warp): try_wait with a suspend-time
+// hint, so that the warp sleeps in hardware instead of re-issuing the test (the plain try_wait loop of eight producer
+// warps took a quarter of all issue slots of the kernel)
+__device__ __forceinline__ void fbq_mbar_wait_idle(unsigned bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "FBQ_IWAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+        "@p bra FBQ_IDONE;\n"
+        "bra FBQ_IWAIT;\n"
+        "FBQ_IDONE:\n"
+        "}\n" ::"r"(bar), "r"(parity), "r"(100000u) : "memory");
 }
 // The requests of one chunk, by one elected lane of the (converged) warp: arm the stage's mbarrier with the bytes of
 // both boxes, then two TMA tensor loads of a box of 32 doubles x 8 rows: rows c1n .. c1n+7 to dst, rows c1o .. c1o+7
@@ -126,6 +148,19 @@ __device__ __forceinline__ void fbq_fence_async() { asm volatile("fence.proxy.as
 __device__ __forceinline__ void fbq_tmem_st2(unsigned taddr, unsigned r0, unsigned r1)
 {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr), "r"(r0), "r"(r1) : "memory");
+}
+
+__device__ __forceinline__ void fbq_mbar_arrive(unsigned bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void fbq_sts4(unsigned addr, int a, int b, int c, int d)
+{
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void fbq_lds4(unsigned addr, int &a, int &b, int &c, int &d)
+{
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(addr) : "memory");
 }
 
 __device__ __forceinline__ double fbq_lds(unsigned addr)
@@ -517,6 +552,335 @@ fb_sweepq_kernel(const FbSweepQ p, const __grid_constant__ CUtensorMap tm_in, co
     }   // persistent loop
 
     if (MODE == 0 || MODE == 1) fbq_bulk_wait0();
+    if constexpr (NT > 0) {
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (wid == 0)
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(s_tmem_base), "r"((unsigned)p.tmem_alloc_cols) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Transposing x sweep fed by the binned samples (fb_sparse.cuh) instead of a dense injection grid.
+//
+// The pass warps are those of fb_sweepq_kernel<.., 1> (same arithmetic, rings, transposing TMA store); what differs is
+// where the rows come from.  One producer warp per pass warp of node entries (sorted
+// by row) with two cursors -- the rows t .. t+7 and the rows D = 2T+2 further back that pass 1 subtracts -- and writes
+// them as 2 KB tiles of zeros with the nodes scattered in (st.shared), NST chunks ahead.  Per staging slot an mbarrier
+// `full` (16 arrivals: the lanes of the producer's half warp) and `empty` (32 arrivals: the pass warp's lanes, right after it has loaded
+// the slot into registers) do the hand-over; a 16-byte header per slot carries {outer, group, stream position, flags}, so
+// that the pass warps are driven by what arrives (the producers claim the work items).  93 % of the bench grid is zeros:
+// the 16 B per grid point the dense sweep reads, and the 16 B per grid point the zero-fill writes, are never moved.
+//   a pass warp's block of shared memory: +0 full[8]   +64 empty[8]   +128 headers[8 x 16 B]   +256 stages   rings
+#define FBQS_FULL 0u
+#define FBQS_EMPTY 64u
+#define FBQS_HEAD 128u
+#define FBQS_STAGES 256u
+#define FBQS_FLAG_STOP 1
+#define FB_BIN_END 0xfffffffeu
+
+// A producer warp serves two pass warps AT THE SAME TIME: lanes 0-15 work for the first, lanes 16-31 for the second
+// (all state is per lane and uniform inside a half warp).  Per pass warp it keeps, in shared memory,
+//   * the line group's row of bin_start (first entry of every bucket; one bulk copy per line group), and
+//   * FBQS_PF prefetch slots of 2 x 16 entries (FbRec, 32 bytes): the entries of the rows a .. a+7 are those of one bucket
+//     (or of two neighbouring ones when the window straddles a bucket boundary), i.e. ONE contiguous range of the record
+//     array, fetched with `cp.async.bulk` one chunk ahead and counted in bytes on the slot's mbarrier.
+// So nothing is searched and no load result waits in a register across a loop iteration (register prefetches of this
+// kind stalled on the scoreboard they share with the loads issued a moment ago: the wait for an old load is a wait for
+// all of them).  The scatter of a window is one predicated 16-byte shared-memory store per lane; windows with more than
+// 16 entries (clustered observations) take the rest with plain loads.
+#define FBQS_PF 2                 // prefetch slots per pass warp
+#define FBQS_PF_BYTES 1024u       // one slot: 16 entries of the new rows + 16 entries of the old rows
+
+__device__ __forceinline__ void fbq_bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar) : "memory");
+}
+
+// entry range of the rows a .. a+7 from the line group's bucket table in shared memory
+__device__ __forceinline__ void fbq_window_range(unsigned table, int nb, int a, int t_begin, unsigned &s0, unsigned &s1)
+{
+    const int rel = a - t_begin;                         // multiple of 8 for the new rows; any value for the old rows
+    int m0 = rel >= 0 ? rel >> 3 : -((-rel + 7) >> 3);   // floor(rel / 8)
+    int m1 = m0 + ((rel & 7) ? 2 : 1);                   // one bucket behind the last one touched
+    m0 = m0 < 0 ? 0 : m0;
+    m1 = m1 > nb ? nb : m1;
+    s0 = s1 = 0u;
+    if (m0 < m1) {
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(s0) : "r"(table + 4u * (unsigned)m0) : "memory");
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(s1) : "r"(table + 4u * (unsigned)m1) : "memory");
+    }
+}
+
+// scatter the nodes of rows a .. a+7 into the (zeroed) tile: row r at 256 * (r - a), line y at 16 * y, (vg, wg) as a pair.
+// The first 16 entries of [s0, s1) sit in the prefetch slot `pf`, further ones are read from global memory.
+__device__ __forceinline__ void fbq_window_scatter(const FbSweepQ &p, unsigned s0, unsigned s1, unsigned pf, int a, unsigned tile, int hl)
+{
+    for (unsigned base = s0; base < s1; base += 16u) {   // uniform inside the half warp
+        const unsigned idx = base + (unsigned)hl;
+        unsigned pos = FB_BIN_END, pad;
+        double v = 0.0, w = 0.0;
+        if (idx < s1) {
+            if (base == s0) {
+                unsigned wlo, whi;
+                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(pos), "=r"(pad), "=r"(wlo), "=r"(whi) : "r"(pf + 32u * (unsigned)hl) : "memory");
+                asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(pf + 32u * (unsigned)hl + 16u) : "memory");
+                w = __hiloint2double((int)whi, (int)wlo);
+            } else {
+                const FbRec *r = p.nodes + idx;
+                pos = r->key;
+                w = r->w;
+                v = r->wv;
+            }
+        }
+        const int row = (int)(pos >> 4);
+        if (pos < FB_BIN_END && row >= a && row < a + FBQ_U) {       // not a hole, not beyond the range, inside the window
+            const unsigned addr = tile + (unsigned)(row - a) * 256u + (pos & 15u) * 16u;
+            asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(v), "d"(w) : "memory");
+        }
+    }
+}
+
+template <int NPASS, int NS>
+__global__ void __launch_bounds__(512, 1)
+fb_sweepqs_kernel(const FbSweepQ p, const __grid_constant__ CUtensorMap tm_out)
+{
+    constexpr int U = FBQ_U;
+    constexpr int MODE = 1;
+    constexpr int NR = NPASS - 1;
+    constexpr int NT = NR - NS;
+    extern __shared__ __align__(1024) unsigned char fbq_smem[];
+    __shared__ unsigned s_tmem_base;
+
+    const int lane = threadIdx.x & 31;
+    const int wid = __reduce_max_sync(0xffffffffu, (int)(threadIdx.x >> 5));
+    const int ncw = p.ncw;                               // pass warps (8: two warpgroups); as many producer warps follow
+
+    if constexpr (NT > 0) {
+        if (wid == 0) {
+            const unsigned dst = fbq_smem_addr(&s_tmem_base);
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst), "r"((unsigned)p.tmem_alloc_cols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
+    }
+    const unsigned sm0 = fbq_smem_addr(fbq_smem);
+    const unsigned sm_blocks = sm0 + (unsigned)ncw * FBQ_TILE_BYTES;
+    const int nst = p.nst;
+    if (lane == 0 && wid < ncw) {
+        const unsigned blk = sm_blocks + (unsigned)wid * (unsigned)p.smem_per_warp;
+        for (int s = 0; s < nst; ++s) {
+            fbq_mbar_init(blk + FBQS_FULL + 8u * (unsigned)s, 16u);      // the 16 lanes of the producer's half warp
+            fbq_mbar_init(blk + FBQS_EMPTY + 8u * (unsigned)s, 32u);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    fbq_fence_async();
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+    const int L = (int)p.L, T1 = p.T + 1, D = p.D, R = p.R, RP = p.RP;
+    const int lag = NPASS * T1;
+    const int t_begin = -((U - lag % U) % U);
+    const int t_end = L + lag;
+    const int nchunks = (t_end - t_begin + U - 1) / U;
+    const long long n_items = p.n_outer * p.n_groups;
+
+    if (wid >= ncw) {
+        // ================================ producer warp ================================
+        // producer warp ncw + i feeds pass warp i; its two half warps take alternate chunks (half h writes staging slot
+        // h: the pass warp consumes the slots 0, 1, 0, 1, .. across line groups), so two chunks are in production at a time
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 72;" ::: "memory");
+        const int h = lane >> 4, hl = lane & 15;
+        const unsigned hmask = 0xffffu << (16 * h);
+        const int client = wid - ncw;
+        const unsigned blk = sm_blocks + (unsigned)client * (unsigned)p.smem_per_warp;
+        // producer area behind the pass warps' blocks, per pass warp: [mbarriers: table, prefetch slots][bucket table][slots]
+        const unsigned parea = sm_blocks + (unsigned)ncw * (unsigned)p.smem_per_warp + (unsigned)client * (unsigned)p.prod_bytes;
+        const unsigned tbar = parea, pbar = parea + 8u + 8u * (unsigned)h;
+        const unsigned table = parea + 64u;
+        const unsigned pslot = table + (((unsigned)p.nb + 1u) * 4u + 127u) / 128u * 128u + (unsigned)h * FBQS_PF_BYTES;
+        const unsigned ebar = blk + FBQS_EMPTY + 8u * (unsigned)h, fbar = blk + FBQS_FULL + 8u * (unsigned)h;
+        const unsigned head = blk + FBQS_HEAD + 16u * (unsigned)h;
+        const unsigned st = blk + FBQS_STAGES + (unsigned)h * FBQ_STAGE_BYTES;
+        if (lane == 0) {
+            fbq_mbar_init(tbar, 1u);
+            fbq_mbar_init(parea + 8u, 1u);
+            fbq_mbar_init(parea + 16u, 1u);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            fbq_fence_async();
+        }
+        __syncwarp();
+        unsigned epar = 1u;                              // the staging slot starts free: parity 1 passes on a fresh barrier
+        unsigned tpar = 0u, ppar = 0u;                   // parities of the table barrier / this half's prefetch barrier
+        unsigned gbase = 0u;                             // chunks this pass warp has been fed so far (slot = chunk & 1)
+        // request the first 16 entries of both windows of the chunk at stream position tt into this half's prefetch slot
+        auto prefetch = [&](int tt) {
+            unsigned n0, n1, o0, o1;
+            fbq_window_range(table, p.nb, tt, t_begin, n0, n1);
+            fbq_window_range(table, p.nb, tt - D, t_begin, o0, o1);
+            if (hl == 0) {
+                const unsigned cn = (n1 - n0 < 16u ? n1 - n0 : 16u) * 32u, co = (o1 - o0 < 16u ? o1 - o0 : 16u) * 32u;
+                fbq_mbar_expect_tx(pbar, cn + co);
+                if (cn) fbq_bulk_g2s(pslot, p.nodes + n0, cn, pbar);
+                if (co) fbq_bulk_g2s(pslot + 512u, p.nodes + o0, co, pbar);
+            }
+        };
+#pragma unroll 1
+        for (;;) {
+            // claim the next 16-line group for this pass warp
+            unsigned long long claimed = 0;
+            if (lane == 0) claimed = atomicAdd(p.work_counter, 1ull);
+            claimed = __shfl_sync(0xffffffffu, claimed, 0);
+            if ((long long)claimed >= n_items) {
+                if (h == (int)(gbase & 1u)) {            // the slot the pass warp looks at next
+                    fbq_mbar_wait(ebar, epar);
+                    if (hl == 0) fbq_sts4(head, 0, 0, 0, FBQS_FLAG_STOP);
+                    fbq_mbar_arrive(fbar);
+                }
+                break;
+            }
+            const int outer = (int)((long long)claimed / p.n_groups);
+            const int group = (int)((long long)claimed - (long long)outer * p.n_groups);
+            // the line group's bucket table (nb + 1 entries; the copy is a multiple of 16 bytes: the array is padded)
+            if (lane == 0) {
+                const unsigned bytes = (((unsigned)p.nb + 1u) * 4u + 15u) & ~15u;
+                fbq_mbar_expect_tx(tbar, bytes);
+                fbq_bulk_g2s(table, p.bin_start + ((long long)outer * p.n_groups + group) * p.nb, bytes, tbar);
+            }
+            fbq_mbar_wait(tbar, tpar);
+            tpar ^= 1u;
+            int c = h ^ (int)(gbase & 1u);               // this half's first chunk of the line group
+            if (c < nchunks) prefetch(t_begin + c * U);
+#pragma unroll 1
+            for (; c < nchunks; c += 2) {
+                const int t = t_begin + c * U;
+                // rows t .. t+7 (new) and t-D .. t-D+7 (old) into this half's staging slot
+                fbq_mbar_wait_idle(ebar, epar);
+                epar ^= 1u;
+#pragma unroll
+                for (int k = 0; k < 16; ++k)
+                    asm volatile("st.shared.v2.f64 [%0], {%1, %1};" ::"r"(st + (unsigned)(k * 16 + hl) * 16u), "d"(0.0) : "memory");
+                unsigned n0, n1, o0, o1;
+                fbq_window_range(table, p.nb, t, t_begin, n0, n1);
+                fbq_window_range(table, p.nb, t - D, t_begin, o0, o1);
+                fbq_mbar_wait(pbar, ppar);
+                ppar ^= 1u;
+                __syncwarp(hmask);                       // the zeros of all 16 lanes are in place
+                fbq_window_scatter(p, n0, n1, pslot, t, st, hl);
+                fbq_window_scatter(p, o0, o1, pslot + 512u, t - D, st + 2048u, hl);
+                __syncwarp(hmask);                       // the prefetch slot has been read
+                if (c + 2 < nchunks) prefetch(t + 2 * U);
+                if (hl == 0) fbq_sts4(head, outer, group, t, 0);
+                fbq_mbar_arrive(fbar);
+            }
+            __syncwarp();
+            gbase += (unsigned)nchunks;
+        }
+        if constexpr (NT > 0) {
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncthreads();
+        }
+        return;
+    }
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 176;" ::: "memory");
+
+    // ================================== pass warp ==================================
+    const unsigned tile = sm0 + (unsigned)wid * FBQ_TILE_BYTES;
+    const unsigned wsm = sm_blocks + (unsigned)wid * (unsigned)p.smem_per_warp;
+    const unsigned stages = wsm + FBQS_STAGES;
+    const unsigned ring_s = wsm + (unsigned)p.off_ring + (unsigned)lane * 8u;
+    unsigned tring = 0;
+    if constexpr (NT > 0)
+        tring = s_tmem_base + ((unsigned)((wid & 3) * 32) << 16) + (unsigned)((wid >> 2) * p.tmem_cols_per_warp);
+    const unsigned rp_bytes = (unsigned)RP * 256u, rp_cols = 2u * (unsigned)RP;
+    const bool has_mirror = RP > R;
+    const double alpha = p.alpha;
+    const int fld = lane & 1;
+    const unsigned tile_lane = tile + (unsigned)(lane >> 1) * 128u + (unsigned)fld * 8u;
+    const unsigned tile_xor = (unsigned)((lane >> 1) & 7) << 4;
+
+    double accu[NPASS], new0[NPASS], xsp[U];
+#pragma unroll
+    for (int q = 0; q < NPASS; ++q) { accu[q] = 0.0; new0[q] = 0.0; }
+#pragma unroll
+    for (int j = 0; j < U; ++j) xsp[j] = 0.0;
+    unsigned fpar = 0;
+    int slot = 0, wslot = 0, rslot = 0;
+    bool pend = false;                                   // xsp holds rows pend_kb .. of (pend_outer, pend_group) not yet stored
+    int pend_outer = 0, pend_group = 0, pend_kb = 0;
+
+    auto emit = [&](const double (&x)[U], int outer, int group, int kb) {
+        fbq_bulk_wait_read0();
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < U; ++j) fbq_sts(tile_lane + (((unsigned)j << 4) ^ tile_xor), x[j]);
+        fbq_fence_async();
+        __syncwarp();
+        fbq_tma_store(&tm_out, 2 * kb, group * 16, outer, tile);
+    };
+
+#pragma unroll 1
+    for (;;) {
+        fbq_mbar_wait(wsm + FBQS_FULL + 8u * (unsigned)slot, (fpar >> slot) & 1u);
+        fpar ^= 1u << slot;
+        int h_outer, h_group, t, h_flags;
+        fbq_lds4(wsm + FBQS_HEAD + 16u * (unsigned)slot, h_outer, h_group, t, h_flags);
+        // the header is the same for all lanes: through redux.sync into uniform registers (TMA operands, branches)
+        const int outer = __reduce_max_sync(0xffffffffu, h_outer);
+        const int group = __reduce_max_sync(0xffffffffu, h_group);
+        t = __reduce_max_sync(0xffffffffu, t + 0x40000000) - 0x40000000;      // t may be negative
+        if (__reduce_max_sync(0xffffffffu, h_flags) & FBQS_FLAG_STOP) break;
+        if (t == t_begin) {
+            // first chunk of a line group: rings and pass state start as zeros
+            if constexpr (NT > 0) {
+                unsigned z[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) z[i] = 0u;
+                for (int i = 0; i < NT * RP; i += 8) fb_tmem_st16(tring + 2u * (unsigned)i, z);
+                fb_tmem_wait_st();
+            }
+            if constexpr (NS > 0) {
+                for (int i = 0; i < NS * RP; ++i) fbq_sts(ring_s + (unsigned)i * 256u, 0.0);
+            }
+#pragma unroll
+            for (int q = 0; q < NPASS; ++q) { accu[q] = 0.0; new0[q] = 0.0; }
+            wslot = 0;
+            rslot = (R - D % R) % R;
+            __syncwarp();
+        }
+        const unsigned stn = stages + (unsigned)slot * FBQ_STAGE_BYTES + (unsigned)lane * 8u;
+        const unsigned sto = stn + 2048u;
+        double bn[U], bo[U], xs[U];
+#pragma unroll
+        for (int j = 0; j < U; ++j) bn[j] = fbq_lds(stn + (unsigned)j * 256u);
+#pragma unroll
+        for (int j = 0; j < U; ++j) bo[j] = fbq_lds(sto + (unsigned)j * 256u);
+        fbq_mbar_arrive(wsm + FBQS_EMPTY + 8u * (unsigned)slot);       // the slot is in registers: the producer may refill it
+        const unsigned sr = ring_s + (unsigned)rslot * 256u, sw = ring_s + (unsigned)wslot * 256u;
+        const unsigned tr = tring + 2u * (unsigned)rslot, tw = tring + 2u * (unsigned)wslot;
+        const bool mirror = has_mirror && wslot == 0;
+        const bool fast = (t - U >= lag) && (t + U - 1 - T1 < L);
+        if (fast) {
+            fbq_chunk<NPASS, NS, false>(bn, bo, accu, new0, xs, sr, sw, rp_bytes, tr, tw, rp_cols, mirror, (unsigned)R, t, T1, L, alpha);
+            emit(xsp, pend_outer, pend_group, pend_kb);  // on the fast path the previous chunk always left rows
+        } else {
+            fbq_chunk<NPASS, NS, true>(bn, bo, accu, new0, xs, sr, sw, rp_bytes, tr, tw, rp_cols, mirror, (unsigned)R, t, T1, L, alpha);
+            if (pend) emit(xsp, pend_outer, pend_group, pend_kb);
+        }
+        if constexpr (NT > 0) fb_tmem_wait_st();
+        const int kb = t - lag;
+        pend = kb >= 0 && kb < L;
+        pend_outer = outer; pend_group = group; pend_kb = kb;
+#pragma unroll
+        for (int j = 0; j < U; ++j) xsp[j] = xs[j];
+        wslot += U; wslot = (wslot >= R) ? 0 : wslot;
+        rslot += U; rslot = (rslot >= R) ? rslot - R : rslot;
+        ++slot; slot = (slot == nst) ? 0 : slot;
+    }
+    if (pend) emit(xsp, pend_outer, pend_group, pend_kb);
+    fbq_bulk_wait0();
     if constexpr (NT > 0) {
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();

@@ -942,3 +942,46 @@ def test_spare_buffers_after_interleaved_x_sweep(fb, orc):
     a = fb.barnes(pts3, val3, sig3, [0.0, 0.0, 0.0], step, size3, num_iter=n3)
     ref = orc.barnes(pts3, val3, sig3, [0.0, 0.0, 0.0], step, size3, num_iter=n3, nthreads=8)
     assert bits_equal(a, ref)
+
+
+def test_sparse_injection_feeds_the_x_sweep(fb, orc):
+    """ opt-in path `sparse_inject`: the samples are binned by the x sweep's unit of work (sort by cell: count, scan,
+    fill; one ordered segmented reduce per bucket) and producer warps turn the node entries into the rows the passes
+    read -- no dense injection grid.  Bit for bit against the dense path and the oracle: repeated locations, a field with
+    all samples in one cell (one bucket with 6000 records), samples outside the grid, ragged fields. """
+    torch = pytest.importorskip('torch')
+    from fastbarnes import _lib
+    L = _lib.lib()
+    rng = np.random.default_rng(909)
+    F, N = 40, 1500
+    size = (512, 500)
+    step = 0.125
+    ext = np.asarray([(size[0] - 1) * step, (size[1] - 1) * step])
+    pts = rng.uniform(-0.03, 1.03, (F, N, 2)) * ext
+    pts[0, :100] = pts[0, 100:200]
+    pts[1, :600] = pts[1, 600:625].repeat(24, axis=0)
+    pts[2] = (np.asarray([200.25, 300.75]) + rng.uniform(0, 0.5, (N, 2))) * step
+    pts[3, :] = pts[3, 0]
+    val = rng.normal(1000, 10, (F, N))
+    counts = rng.integers(900, N + 1, F)
+    counts[4] = 0
+    counts[5] = 1
+    offs = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    rp = np.concatenate([pts[i, :counts[i]] for i in range(F)])
+    rv = np.concatenate([val[i, :counts[i]] for i in range(F)])
+    d_p, d_v = torch.from_numpy(rp).cuda(), torch.from_numpy(rv).cuda()
+    for n in (4, 3):
+        plan = fb.BarnesDevice(2, 1.0, [0.0, 0.0], step, size, nfields=F, nsamples=int(offs[-1]), num_iter=n, sample_offsets=offs,
+                               want_float64=True)
+        try:
+            _lib.check(L.fb_set_option(b'sparse_inject', 1))
+            a, a64 = plan(d_p, d_v).cpu().numpy(), plan.out64.cpu().numpy()
+        finally:
+            L.fb_set_option(b'sparse_inject', 0)
+        b, b64 = plan(d_p, d_v).cpu().numpy(), plan.out64.cpu().numpy()
+        assert bits_equal(a, b) and bits_equal(a64, b64), n
+        assert np.isnan(a[4]).all()
+        for i in (0, 1, 2, 3, 5, F - 1):
+            lo, hi = int(offs[i]), int(offs[i + 1])
+            ref = orc.barnes(rp[lo:hi], rv[lo:hi], 1.0, [0.0, 0.0], step, size, num_iter=n, nthreads=4)
+            assert bits_equal(a[i], ref), (n, i)

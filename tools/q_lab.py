@@ -128,9 +128,8 @@ def timing(settings=None):
     if settings is None:
         settings = [
             dict(sweepq=0),
-            dict(sweepq=1, sweepq_stages=3, sweepq_finalize_warps=1),
-            dict(sweepq=1, sweepq_stages=3, sweepq_finalize_warps=0),
-            dict(sweepq=1, sweepq_stages=2, sweepq_finalize_warps=1),
+            dict(sweepq=1, sparse_inject=0),
+            dict(sweepq=1, sparse_inject=1),
         ]
     ref = None
     results = []
@@ -164,7 +163,7 @@ def timing(settings=None):
                     'equal_to_first': bits_equal(o, ref)})
         results.append(rec)
         print(json.dumps(rec), flush=True)
-    set_opts(L, sweepq=1, sweepq_stages=3, sweepq_finalize_warps=1)
+    set_opts(L, sweepq=1, sparse_inject=1)
     return results
 
 
