@@ -10,6 +10,7 @@
 #include "fb_exact.cuh"
 #include "fb_sweep32.cuh"
 #include "fb_sweepq.cuh"
+#include "fb_line1d.cuh"
 
 #include <atomic>
 #include <cmath>
@@ -40,6 +41,7 @@ std::atomic<int> g_two_warp{1};     // tuning switch (fb_set_option): two-warp s
 std::atomic<int> g_sweepq{1};
 std::atomic<int> g_q_nst{3};        // staging slots (chunks of rows in flight) per warp
 std::atomic<int> g_q_pf{0};         // extra chunks of lead of the L2 prefetch (0: none)
+std::atomic<int> g_line1d{1};       // 1D grids: the two-warp line kernel (fb_line1d.cuh) for the exact walk
 std::atomic<int> g_q_warps{8};      // warps per CTA the plan starts with (8 or 4)
 // q path: injection as sort by cell + segmented reduce feeding the x sweep (fb_sparse.cuh) instead of dense grids
 std::atomic<int> g_sparse{0};       // opt-in: measured slower than the dense path (x sweep 1.55 vs 1.15 ms on the bench batch), see DESIGN.md
@@ -1288,6 +1290,51 @@ bool inject_interleaved(const fb_problem *pr, const Derived &d)
     return sweep_is_single_hybrid(1, pr->num_iter, d.ax[0].T, (long long)pr->nfields * d.Dz, d.H);
 }
 
+// ---- 1D grids: the bit-exact walk of a long line (fb_line1d_kernel) ------------------------------------------------
+struct Line1DPlan { bool ok; int DL, RL; size_t smem; };
+Line1DPlan line1d_plan(int npass, int T)
+{
+    Line1DPlan q{false, 0, 0, 0};
+    if (npass < 1 || npass > FB_MAX_FUSED_PASSES) return q;
+    const int T1 = T + 1, D = 2 * T + 2;
+    q.DL = (T1 + FBL_U - 1) / FBL_U + 1;
+    const int ahead = q.DL > FBL_PD ? q.DL : FBL_PD;
+    int need = D + FBL_U * (ahead + 3), rl = 64;
+    while (rl < need) rl *= 2;
+    q.RL = rl;
+    q.smem = (size_t)2 * (npass + 1) * (rl + 2) * sizeof(double);       // rings are staggered by 2 doubles (bank conflicts)
+    q.ok = q.smem <= kSmemLimit;
+    return q;
+}
+
+template <int NPASS>
+int launch_line1d_t(const FbLine1D &p, const Line1DPlan &q, long long nfields, cudaStream_t st)
+{
+    static thread_local bool configured[16] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!configured[dev & 15]) {
+        CUDA_TRY(cudaFuncSetAttribute(fb_line1d_kernel<NPASS, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+        configured[dev & 15] = true;
+    }
+    fb_line1d_kernel<NPASS, 2><<<(unsigned)nfields, 64, q.smem, st>>>(p);
+    LAUNCH_CHECK();
+    return FB_OK;
+}
+
+int launch_line1d(int npass, const FbLine1D &p, const Line1DPlan &q, long long nfields, cudaStream_t st)
+{
+    switch (npass) {
+    case 1: return launch_line1d_t<1>(p, q, nfields, st);
+    case 2: return launch_line1d_t<2>(p, q, nfields, st);
+    case 3: return launch_line1d_t<3>(p, q, nfields, st);
+    case 4: return launch_line1d_t<4>(p, q, nfields, st);
+    case 5: return launch_line1d_t<5>(p, q, nfields, st);
+    case 6: return launch_line1d_t<6>(p, q, nfields, st);
+    }
+    return fail(FB_EINVAL, "unsupported number of fused passes: %d", npass);
+}
+
 int run_sweeps(const fb_problem *pr, const Derived &d, Workspace &w, float *d_out, double *d_out64, cudaStream_t st,
                const SegPlan &sp, bool sparse = false)
 {
@@ -1312,6 +1359,17 @@ int run_sweeps(const fb_problem *pr, const Derived &d, Workspace &w, float *d_ou
         return prof_mark(3, st);
     }
     if (pr->dim == 1) {
+        const Line1DPlan lq = line1d_plan(n, d.ax[0].T);
+        if (g_line1d.load() != 0 && lq.ok && d.W >= 1024 && nf <= 65535) {
+            // long lines: the 2 n (field, pass) chains as lanes of one warp, a second warp feeds and finalises
+            FbLine1D p{};
+            p.in_v = cur.v; p.in_w = cur.w; p.out_v = p.out_w = nullptr; p.out32 = d_out; p.out64 = d_out64; p.mm = w.mm;
+            p.L = d.W; p.T = d.ax[0].T; p.D = 2 * d.ax[0].T + 2; p.DL = lq.DL; p.RL = lq.RL;
+            p.alpha = d.ax[0].alpha; p.csf = d.csf;
+            rc = launch_line1d(n, p, lq, nf, st);
+            if (rc != FB_OK) return rc;
+            return prof_mark(3, st);
+        }
         rc = run_sweep(2, n, d.ax[0], cur, spare, d_out, d_out64, w.mm, d.csf, nf, d.W, 1, true, st, ctr);
         if (rc != FB_OK) return rc;
         return prof_mark(3, st);
@@ -2355,6 +2413,7 @@ FB_EXPORT int fb_set_option(const char *name, int value)
     if (!strcmp(name, "sweepq_prefetch")) { g_q_pf.store(value); return FB_OK; }
     if (!strcmp(name, "sweepq_warps")) { g_q_warps.store(value); return FB_OK; }
     if (!strcmp(name, "sparse_inject")) { g_sparse.store(value); return FB_OK; }
+    if (!strcmp(name, "line1d")) { g_line1d.store(value); return FB_OK; }
     return fail(FB_EINVAL, "unknown option: %s", name);
 }
 

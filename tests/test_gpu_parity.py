@@ -421,39 +421,65 @@ def test_properties_full_size(fb):
     assert np.allclose(b[~np.isnan(b)], 2.0 * a[~np.isnan(a)], rtol=3e-7, atol=0)
 
 
-def test_1d_segmented_vs_exact(fb, orc):
-    """ 1D: the default for long grids cuts the single line into overlapping segments.  Exact in
-    exact arithmetic; vs the reference the fp64 quotient differs by the reference's own accumulated
-    rounding (its accumulator runs over the whole line; grows ~sqrt(L)).  Tolerance: 1e-8 * value
-    range on the fp64 quotient for L = 2^18, NaN mask identical, float32 identical on > 99.9 % of
-    the points and within 8 ulp everywhere.  exact=True stays bit-identical. """
+def test_1d_exact_default_and_segmented_option(fb, orc):
+    """ 1D: the default walks the single line with the 2 x num_iter (field, pass) chains side by side
+    (csrc/fb_line1d.cuh) and is BIT-IDENTICAL to the reference at any length, for every pass count, kernel width
+    (T = 1 .. 55) and for lines whose length is no multiple of the chunk.  exact=False opts into overlapping segments
+    swept in parallel: exact in exact arithmetic; vs the reference the fp64 quotient then differs by the reference's
+    own accumulated rounding (tolerance 1e-8 * value range at 2^18 points, NaN mask identical, float32 within 8 ulp). """
     rng = np.random.default_rng(1234)
     L = 2 ** 18
     N = L // 64
     pts = rng.uniform(0, L - 1, N)
     val = rng.normal(0, 1, N)
     vrange = val.max() - val.min()
-    for n, sigma in ((4, 32.0), (6, 32.0), (5, 3.0), (1, 10.0)):
+    for n, sigma in ((4, 32.0), (6, 32.0), (5, 3.0), (1, 10.0), (2, 64.0), (3, 1.2)):
         ref = orc._interpolate_opt_convol(pts.reshape(-1, 1), val.copy(), np.asarray([sigma]), np.zeros(1), np.ones(1),
                                           (L,), n, exp(-3.5 ** 2 / 2), stages=True)
-        a32, a64 = fb.barnes(pts, val, sigma, 0.0, 1.0, L, num_iter=n, return_float64=True)      # default: segmented
-        assert np.array_equal(np.isnan(a64), np.isnan(ref['out64']))
-        m = ~np.isnan(ref['out64'])
-        assert np.max(np.abs(a64[m] - ref['out64'][m])) <= 1e-8 * vrange, (n, sigma)
-        assert np.mean(a32[m] != ref['out32'][m]) < 1e-3
-        ulp = np.abs(a32[m].view(np.int32).astype(np.int64) - ref['out32'][m].view(np.int32).astype(np.int64))
-        assert ulp.max() <= 8
-        if n == 4:
-            e32, e64 = fb.barnes(pts, val, sigma, 0.0, 1.0, L, num_iter=n, return_float64=True, exact=True)
-            assert bits_equal(e64, ref['out64']) and bits_equal(e32, ref['out32'])
-    # short grids take the exact path by default
-    Ls = 5000
-    p2 = rng.uniform(0, Ls - 1, 200)
-    v2 = rng.normal(5, 2, 200)
-    assert bits_equal(fb.barnes(p2, v2, 12.0, 0.0, 1.0, Ls), orc.barnes(p2.reshape(-1, 1), v2, 12.0, 0.0, 1.0, (Ls,)))
-    seg = fb.barnes(p2, v2, 12.0, 0.0, 1.0, Ls, exact=False)               # forcing segments on a short grid works too
+        e32, e64 = fb.barnes(pts, val, sigma, 0.0, 1.0, L, num_iter=n, return_float64=True)          # default: exact
+        assert bits_equal(e64, ref['out64']) and bits_equal(e32, ref['out32']), (n, sigma)
+        if n in (4, 1):
+            a32, a64 = fb.barnes(pts, val, sigma, 0.0, 1.0, L, num_iter=n, return_float64=True, exact=False)
+            assert np.array_equal(np.isnan(a64), np.isnan(ref['out64']))
+            m = ~np.isnan(ref['out64'])
+            assert np.max(np.abs(a64[m] - ref['out64'][m])) <= 1e-8 * vrange, (n, sigma)
+            assert np.mean(a32[m] != ref['out32'][m]) < 1e-3
+            ulp = np.abs(a32[m].view(np.int32).astype(np.int64) - ref['out32'][m].view(np.int32).astype(np.int64))
+            assert ulp.max() <= 8
+    # odd lengths, the old lane-pair walk as a cross-check, short grids
+    from fastbarnes import _lib
+    for Ls in (5000, 1025, 77777):
+        p2 = rng.uniform(0, Ls - 1, Ls // 25)
+        v2 = rng.normal(5, 2, Ls // 25)
+        a = fb.barnes(p2, v2, 12.0, 0.0, 1.0, Ls)
+        assert bits_equal(a, orc.barnes(p2.reshape(-1, 1), v2, 12.0, 0.0, 1.0, (Ls,))), Ls
+        try:
+            _lib.check(_lib.lib().fb_set_option(b'line1d', 0))
+            assert bits_equal(a, fb.barnes(p2, v2, 12.0, 0.0, 1.0, Ls)), Ls
+        finally:
+            _lib.lib().fb_set_option(b'line1d', 1)
+    seg = fb.barnes(p2, v2, 12.0, 0.0, 1.0, Ls, exact=False)               # forcing segments works too
     ex = fb.barnes(p2, v2, 12.0, 0.0, 1.0, Ls)
     assert np.array_equal(np.isnan(seg), np.isnan(ex)) and np.nanmax(np.abs(seg - ex)) <= 1e-5
+
+
+def test_1d_exact_2e22_points_is_fast(fb, orc):
+    """ BASELINE configs[1] at 1/16 of its length: N = 65536 samples on a 2^22-point line, sigma 32 (T = 27), n = 4:
+    bit-identical to the oracle, and the device pipeline stays below 60 ms (the lane-pair walk needed ~590 ms, the
+    reference's Numba code ~290 ms for this length) """
+    import time
+    rng = np.random.default_rng(1234)
+    L = 2 ** 22
+    N = L // 64
+    pts = rng.uniform(0, L - 1, N)
+    val = rng.normal(0, 1, N)
+    ref = orc.barnes(pts.reshape(-1, 1), val, 32.0, 0.0, 1.0, (L,), num_iter=4, nthreads=8)
+    a = fb.barnes(pts, val, 32.0, 0.0, 1.0, L, num_iter=4)
+    assert bits_equal(a, ref)
+    t0 = time.perf_counter()
+    fb.barnes(pts, val, 32.0, 0.0, 1.0, L, num_iter=4)
+    dt = time.perf_counter() - t0
+    assert dt < 0.060, dt
 
 
 def test_z_slab_decomposition_single_gpu(fb):
