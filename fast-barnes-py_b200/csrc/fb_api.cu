@@ -2109,16 +2109,19 @@ FB_EXPORT int fb_slab_layout(const fb_problem *prob, int64_t nsamples, int64_t z
     return FB_OK;
 }
 
-FB_EXPORT int fb_slab_phase1_dev(const fb_problem *prob, int64_t z_begin, int64_t z_count, int64_t halo_lo, int64_t halo_hi,
-                                 int64_t nsamples, const double *d_pts, const double *d_val, int want_out64,
-                                 void *d_workspace, int64_t workspace_bytes, void *stream)
+namespace {
+// injection (do_inject) and / or the x and y sweeps of the own planes [pb, pb + pc) of a slab
+int slab_phase1(const fb_problem *prob, int64_t z_begin, int64_t z_count, int64_t halo_lo, int64_t halo_hi, int64_t nsamples,
+                const double *d_pts, const double *d_val, int want_out64, void *d_workspace, int64_t workspace_bytes,
+                void *stream, bool do_inject, long long pb, long long pc)
 {
     int rc = require_device();
     if (rc != FB_OK) return rc;
     Derived d;
     if ((rc = slab_check(prob, d, z_begin, z_count, halo_lo, halo_hi)) != FB_OK) return rc;
     if ((rc = check_kernel_vs_grid(prob, d)) != FB_OK) return rc;
-    if (!d_pts || !d_val || !d_workspace) return fail(FB_EINVAL, "null device pointer");
+    if (!d_workspace || (do_inject && (!d_pts || !d_val))) return fail(FB_EINVAL, "null device pointer");
+    if (pb < 0 || pc < 0 || pb + pc > z_count) return fail(FB_EINVAL, "plane range [%lld, %lld) outside the slab", pb, pb + pc);
     const long long z_ext = z_count + halo_lo + halo_hi;
     SlabLayout s;
     slab_carve(s, (char *)d_workspace, prob, d, nsamples, z_ext, want_out64 != 0);
@@ -2131,19 +2134,46 @@ FB_EXPORT int fb_slab_phase1_dev(const fb_problem *prob, int64_t z_begin, int64_
     w.wA = s.wA + halo_lo * plane;
     w.vB = s.vB + halo_lo * plane;
     w.wB = s.wB + halo_lo * plane;
-    if ((rc = run_inject(prob, d, nsamples, nullptr, d_pts, d_val, w, st, z_begin, z_count)) != FB_OK) return rc;
-    // x sweep (A -> B, transposing) and y sweep (in place) on the own planes
-    Pair cur{w.vA, w.wA}, spare{w.vB, w.wB};
+    if (do_inject && (rc = run_inject(prob, d, nsamples, nullptr, d_pts, d_val, w, st, z_begin, z_count)) != FB_OK) return rc;
+    if (pc == 0) return FB_OK;
+    // x sweep (A -> B, transposing) and y sweep (in place) on the planes [pb, pb + pc)
+    Pair cur{w.vA + pb * plane, w.wA + pb * plane}, spare{w.vB + pb * plane, w.wB + pb * plane};
+    double *home_v = spare.v, *home_w = spare.w;
     SweepCounters ctr{w.counters + 4, 0};
-    rc = run_sweep(1, prob->num_iter, d.ax[0], cur, spare, nullptr, nullptr, w.mm, d.csf, z_count, d.W, d.H, true, st, ctr);
+    rc = run_sweep(1, prob->num_iter, d.ax[0], cur, spare, nullptr, nullptr, w.mm, d.csf, pc, d.W, d.H, true, st, ctr);
     if (rc != FB_OK) return rc;
-    rc = run_sweep(0, prob->num_iter, d.ax[1], cur, spare, nullptr, nullptr, w.mm, d.csf, z_count, d.H, d.W, true, st, ctr);
+    rc = run_sweep(0, prob->num_iter, d.ax[1], cur, spare, nullptr, nullptr, w.mm, d.csf, pc, d.H, d.W, true, st, ctr);
     if (rc != FB_OK) return rc;
-    if (cur.v != w.vB) {   // per-pass ping-pong may end in the other pair: bring the result home
-        CUDA_TRY(cudaMemcpyAsync(w.vB, cur.v, (size_t)plane * z_count * 8, cudaMemcpyDeviceToDevice, st));
-        CUDA_TRY(cudaMemcpyAsync(w.wB, cur.w, (size_t)plane * z_count * 8, cudaMemcpyDeviceToDevice, st));
+    if (cur.v != home_v) {   // per-pass ping-pong may end in the other pair: bring the result home
+        CUDA_TRY(cudaMemcpyAsync(home_v, cur.v, (size_t)plane * pc * 8, cudaMemcpyDeviceToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(home_w, cur.w, (size_t)plane * pc * 8, cudaMemcpyDeviceToDevice, st));
     }
     return FB_OK;
+}
+}  // namespace
+
+FB_EXPORT int fb_slab_phase1_dev(const fb_problem *prob, int64_t z_begin, int64_t z_count, int64_t halo_lo, int64_t halo_hi,
+                                 int64_t nsamples, const double *d_pts, const double *d_val, int want_out64,
+                                 void *d_workspace, int64_t workspace_bytes, void *stream)
+{
+    return slab_phase1(prob, z_begin, z_count, halo_lo, halo_hi, nsamples, d_pts, d_val, want_out64, d_workspace, workspace_bytes,
+                       stream, true, 0, z_count);
+}
+
+FB_EXPORT int fb_slab_inject_dev(const fb_problem *prob, int64_t z_begin, int64_t z_count, int64_t halo_lo, int64_t halo_hi,
+                                 int64_t nsamples, const double *d_pts, const double *d_val, int want_out64,
+                                 void *d_workspace, int64_t workspace_bytes, void *stream)
+{
+    return slab_phase1(prob, z_begin, z_count, halo_lo, halo_hi, nsamples, d_pts, d_val, want_out64, d_workspace, workspace_bytes,
+                       stream, true, 0, 0);
+}
+
+FB_EXPORT int fb_slab_sweeps_dev(const fb_problem *prob, int64_t z_begin, int64_t z_count, int64_t halo_lo, int64_t halo_hi,
+                                 int64_t nsamples, int want_out64, int64_t plane_begin, int64_t plane_count,
+                                 void *d_workspace, int64_t workspace_bytes, void *stream)
+{
+    return slab_phase1(prob, z_begin, z_count, halo_lo, halo_hi, nsamples, nullptr, nullptr, want_out64, d_workspace,
+                       workspace_bytes, stream, false, plane_begin, plane_count);
 }
 
 FB_EXPORT int fb_slab_phase2_dev(const fb_problem *prob, int64_t z_begin, int64_t z_count, int64_t halo_lo, int64_t halo_hi,

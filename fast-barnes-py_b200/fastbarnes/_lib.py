@@ -62,6 +62,12 @@ SIGNATURES = {
     'fb_slab_phase1_dev': (ctypes.c_int, [ctypes.POINTER(FbProblem), ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
                                           ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
                                           ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]),
+    'fb_slab_inject_dev': (ctypes.c_int, [ctypes.POINTER(FbProblem), ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
+                                          ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                          ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]),
+    'fb_slab_sweeps_dev': (ctypes.c_int, [ctypes.POINTER(FbProblem), ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
+                                          ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_int64, ctypes.c_int64,
+                                          ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]),
     'fb_slab_phase2_dev': (ctypes.c_int, [ctypes.POINTER(FbProblem), ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
                                           ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                           ctypes.c_int64, ctypes.c_void_p]),

@@ -126,6 +126,16 @@ int fb_slab_layout(const fb_problem *prob, int64_t nsamples, int64_t z_count, in
 int fb_slab_phase1_dev(const fb_problem *prob, int64_t z_begin, int64_t z_count, int64_t halo_lo, int64_t halo_hi,
                        int64_t nsamples, const double *d_pts, const double *d_val, int want_out64,
                        void *d_workspace, int64_t workspace_bytes, void *stream);
+/* Phase 1 in two steps, for callers that overlap the halo exchange with the sweeps: fb_slab_inject_dev does the centring
+ * and the injection of all own planes; fb_slab_sweeps_dev then runs the x and y sweeps of the own planes
+ * [plane_begin, plane_begin + plane_count) (relative to z_begin; planes are independent in these sweeps), so that the
+ * planes the neighbours need can be finished -- and sent -- first. */
+int fb_slab_inject_dev(const fb_problem *prob, int64_t z_begin, int64_t z_count, int64_t halo_lo, int64_t halo_hi,
+                       int64_t nsamples, const double *d_pts, const double *d_val, int want_out64,
+                       void *d_workspace, int64_t workspace_bytes, void *stream);
+int fb_slab_sweeps_dev(const fb_problem *prob, int64_t z_begin, int64_t z_count, int64_t halo_lo, int64_t halo_hi,
+                       int64_t nsamples, int want_out64, int64_t plane_begin, int64_t plane_count,
+                       void *d_workspace, int64_t workspace_bytes, void *stream);
 /* Phase 2 (after the halo planes have been filled): z sweep + mask + divide + cast;
  * d_out [z_count][y][x] float32 receives the own planes. */
 int fb_slab_phase2_dev(const fb_problem *prob, int64_t z_begin, int64_t z_count, int64_t halo_lo, int64_t halo_hi,

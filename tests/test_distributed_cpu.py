@@ -94,3 +94,28 @@ def test_single_process_is_plain_call():
     got = distributed.barnes_batched_sharded(pts, val, 0.6, [0.0, 0.0], 0.1, (80, 60), offs, num_iter=3,
                                              compute=_oracle_batched)
     assert bits_equal(got, _oracle_batched(pts, val, 0.6, [0.0, 0.0], 0.1, (80, 60), sample_offsets=offs, num_iter=3))
+
+
+def test_slab_transfer_plan_covers_every_halo_plane():
+    """ z-slab halo exchange plan (fastbarnes.distributed.slab_transfers): for every rank the planes of its extended window
+    that it does not own arrive exactly once, from their owner; sends and receives of the two ends of a transfer agree;
+    slabs thinner than the halo take planes from several ranks. """
+    from fastbarnes.distributed import slab_transfers, shard_range
+    for nplanes, world, halo in ((512, 8, 28), (512, 2, 28), (120, 16, 12), (40, 8, 28), (64, 4, 1), (30, 3, 0)):
+        plans = [slab_transfers(nplanes, world, r, halo) for r in range(world)]
+        for r in range(world):
+            z0, z1 = shard_range(nplanes, world, r)
+            e0, e1 = max(0, z0 - halo), min(nplanes, z1 + halo)
+            got = []
+            for q, send, recv in plans[r]:
+                if recv:
+                    q0, q1 = shard_range(nplanes, world, q)
+                    assert q0 <= recv[0] < recv[1] <= q1            # the sender owns what it sends
+                    got.extend(range(recv[0], recv[1]))
+                    # the peer's plan holds the matching send
+                    assert any(p == r and s == recv for p, s, _ in plans[q])
+                if send:
+                    assert z0 <= send[0] < send[1] <= z1
+                    assert any(p == r and rc == send for p, _, rc in plans[q])
+            want = [z for z in range(e0, e1) if not (z0 <= z < z1)]
+            assert sorted(got) == want, (nplanes, world, halo, r)
