@@ -301,6 +301,93 @@ def extra_blocks(torch, fbi, L, dev):
     return out
 
 
+def slab3d_block(torch, dist, dev, rank, world, steps=5, warmup=2):
+    """ Secondary measurement on ALL ranks: BASELINE configs[2] (C3) -- ONE 1024x1024x512 volume, N=1e7 samples, sigma 8 grid
+    steps, num_iter 4 -- split into z-slabs over the ranks (fastbarnes.distributed.BarnesSlab3D: injection and x / y sweeps of
+    the own planes, halo exchange over NCCL overlapped with the interior sweeps, z sweep + mask + divide + cast).  STRONG
+    scaling: the volume is fixed, the time is the max over ranks of CUDA-event times of whole calls.  Every rank also runs
+    the undivided volume once and compares its own planes (fp64 quotient; |diff| <= 1e-12 * value range, same NaN mask). """
+    from fastbarnes import interpolation as fbi
+    from fastbarnes import distributed as fd
+    W, H, D, N, sigma, n_iter = 1024, 1024, 512, 10_000_000, 8.0, 4
+    rng = np.random.default_rng(1235)                           # the same samples on every rank
+    pts = rng.uniform(0.0, 1.0, (N, 3)) * np.asarray([W - 1, H - 1, D - 1], dtype=np.float64)
+    val = rng.normal(0.0, 1.0, N)
+    dp, dv = torch.from_numpy(pts).to(dev), torch.from_numpy(val).to(dev)
+    slab = fd.BarnesSlab3D(sigma, [0.0] * 3, 1.0, (W, H, D), N, num_iter=n_iter, want_float64=True, device=dev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        slab(dp, dv)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        slab(dp, dv)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / steps
+    # the steps one by one (synchronised between them: no overlap) -- where the time goes
+    parts = np.zeros(4)
+    for _ in range(3):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+        barrier()
+        ev[0].record(); slab.inject(dp, dv)
+        ev[1].record(); slab.sweeps(0, slab.zc)
+        ev[2].record(); slab.exchange()
+        ev[3].record(); slab.phase2()
+        ev[4].record()
+        barrier()
+        parts += [ev[i].elapsed_time(ev[i + 1]) for i in range(4)]
+    parts /= 3
+    own64 = slab.out64.clone()
+    own32 = slab.out.clone()
+    halo, z0, z1 = slab.halo, slab.z0, slab.z1
+    sent = sum((s_[1] - s_[0]) for _, s_, _ in slab.transfers() if s_) * W * H * 16
+    del slab
+    torch.cuda.empty_cache()
+    # the undivided volume on this GPU
+    plan = fbi.BarnesDevice(3, sigma, [0.0] * 3, 1.0, (W, H, D), nfields=1, nsamples=N, num_iter=n_iter, want_float64=True, device=dev)
+    plan(dp, dv)
+    torch.cuda.synchronize()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    plan(dp, dv)
+    f1.record()
+    torch.cuda.synchronize()
+    ms_single = f0.elapsed_time(f1)
+    ref64 = plan.out64.view(D, H, W)[z0:z1]
+    ref32 = plan.out.view(D, H, W)[z0:z1]
+    nan_same = bool(torch.equal(torch.isnan(own64), torch.isnan(ref64)))
+    diff = float(torch.nan_to_num(own64 - ref64, nan=0.0).abs().max())
+    vrange = float(dv.max() - dv.min())
+    f32_same = float((own32.view(torch.int32) == ref32.view(torch.int32)).double().mean())
+    t = torch.tensor([ms, diff, 0.0 if nan_same else 1.0, 1.0 - f32_same, ms_single] + list(parts), dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, diff, nan_bad, f32_diff_frac, ms_single = (float(x) for x in t[:5])
+    parts = [float(x) for x in t[5:]]
+    del plan
+    torch.cuda.empty_cache()
+    return {'workload': 'ONE 1024x1024x512 volume, N=1e7 samples, sigma 8 grid steps, num_iter 4, fp64, device-resident samples; '
+                        'z-slabs over %d GPU(s), halo %d planes per side' % (world, halo),
+            'scaling': 'strong', 'n_gpus': world, 'ms_per_volume': ms, 'value': W * H * D / (ms * 1e-3), 'unit': UNIT,
+            'steps': steps, 'warmup': warmup,
+            'ms_single_gpu_undivided': ms_single,
+            'ms_steps_serialised_max_over_ranks': {'inject': parts[0], 'sweeps_xy': parts[1], 'halo_exchange': parts[2],
+                                                   'sweep_z_finalise': parts[3]},
+            'halo_bytes_sent_rank0': int(sent),
+            'parity_checked': bool(nan_bad == 0.0 and diff <= 1e-12 * vrange),
+            'parity': {'max_abs_diff_fp64_quotient': diff, 'bound': 1e-12 * vrange, 'nan_mask_identical': nan_bad == 0.0,
+                       'float32_bits_differing_fraction': f32_diff_frac,
+                       'against': 'the undivided volume on one GPU (bit-identical to the oracle, tests/test_gpu_parity.py)'}}
+
+
 def run_gpu(args, rank, local_rank, world):
     import torch
     import torch.distributed as dist
@@ -418,6 +505,16 @@ def run_gpu(args, rank, local_rank, world):
     if rank == 0 and world == 1 and not args.no_extra:
         extra = extra_blocks(torch, fbi, L, dev)
 
+    # ---- secondary block on all ranks: the C3 volume as z-slabs (strong scaling) --------------------------
+    slab3d = None
+    if not args.no_extra:
+        try:
+            slab3d = slab3d_block(torch, dist, dev, rank, world)
+        except Exception as e:                       # a secondary block must not take the headline line with it
+            if world > 1:
+                raise                                # ... but a rank that drops out of the collectives must not hang the others
+            slab3d = {'error': repr(e)[:300]}
+
     # ---- end-to-end arm: host buffers through the C ABI -----------------------------------------------
     out_pin = torch.empty((SUB,) + SIZE[::-1], dtype=torch.float32).pin_memory()
     prob = plan.prob
@@ -443,11 +540,26 @@ def run_gpu(args, rank, local_rank, world):
     barrier()
     e2e_s = time.perf_counter() - t0
 
+    # ---- what the host link allows: the result buffer of one sub-batch copied device -> pinned host, all ranks at
+    # the same time (the end-to-end arm moves 4 B per grid point this way and almost nothing the other way) ------------
+    d_out = plan(*d_sets[0])
+    barrier()
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    probe_reps = 4
+    out_pin.copy_(d_out, non_blocking=True)
+    barrier()
+    p0.record()
+    for _ in range(probe_reps):
+        out_pin.copy_(d_out, non_blocking=True)
+    p1.record()
+    barrier()
+    d2h_ms = p0.elapsed_time(p1) / probe_reps
+
     # ---- reduce over ranks (max time) ------------------------------------------------------------------
-    t = torch.tensor([ms_total, e2e_s * 1e3, fp32[0] if fp32 else 0.0], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms_total, e2e_s * 1e3, fp32[0] if fp32 else 0.0, d2h_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, e2e_ms, ms32_total = float(t[0]), float(t[1]), float(t[2])
+    ms_total, e2e_ms, ms32_total, d2h_ms = float(t[0]), float(t[1]), float(t[2]), float(t[3])
     if rank == 0:
         pts_per_step = F * POINTS_PER_FIELD * world
         value = pts_per_step * args.steps / (ms_total * 1e-3)
@@ -478,7 +590,12 @@ def run_gpu(args, rank, local_rank, world):
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d * world, 'd2h_bytes_per_step': d2h * world,
                     'ms_per_step': e2e_ms / e2e_steps, 'steps': e2e_steps,
                     'api': 'fb_barnes_host (C ABI, pinned host buffers, H2D + kernels + D2H inside)',
-                    'host_cpus': numa},
+                    'host_cpus': numa,
+                    # aggregate device -> pinned-host copy rate of the result buffers, all ranks copying at once (max time
+                    # over ranks); the end-to-end arm cannot run faster than its D2H bytes at this rate
+                    'host_ceiling_GBps': out_pin.numel() * 4 * world / (d2h_ms * 1e-3) / 1e9,
+                    'host_ceiling_value': SUB * POINTS_PER_FIELD * world / (d2h_ms * 1e-3),
+                    'frac_of_host_ceiling': (e2e_value * 4 / 1e9) / (out_pin.numel() * 4 * world / (d2h_ms * 1e-3) / 1e9)},
             'gpu_launches': int(launches),
             'roofline': {
                 'bound': 'hbm',
@@ -512,6 +629,8 @@ def run_gpu(args, rank, local_rank, world):
                 'sweep_x_frac_of_peak': bx * pts_launch / (s32[2] * 1e-3) / 1e9 / peak if s32[2] > 0 else 0.0,
                 'sweep_y_frac_of_peak': by * pts_launch / (s32[3] * 1e-3) / 1e9 / peak if s32[3] > 0 else 0.0}
         line.update(extra)
+        if slab3d is not None:
+            line['slab3d'] = slab3d
         if world == 1 and not args.no_cpu:
             cores = os.cpu_count() or 1
             nf = max(cores, 8) * 6          # about 20 core-seconds of CPU work
@@ -572,6 +691,7 @@ def main():
                '--master-addr', '127.0.0.1', '--master-port', str(29500 + os.getpid() % 1000), os.path.abspath(__file__),
                '--gpus', str(args.gpus), '--steps', str(args.steps), '--warmup', str(args.warmup),
                '--fields', str(args.fields), '--streams', str(args.streams)]
+        cmd += [f for f, on in (('--no-extra', args.no_extra), ('--no-cpu', args.no_cpu), ('--no-fp32', args.no_fp32)) if on]
         sys.exit(subprocess.call(cmd, stdout=_JSON_OUT))     # the ranks' stdout is the original stdout
     run_gpu(args, rank, local_rank, world)
 

@@ -2039,6 +2039,7 @@ struct SlabLayout {
     double *out64_ext;
     Workspace inj;                  // injection scratch (record tables, min/max)
     size_t off_vB, off_wB;          // byte offsets of the extended B buffers
+    size_t off_out, off_out64;      // ... and of the extended result buffers
     size_t bytes;
 };
 
@@ -2048,13 +2049,16 @@ int slab_carve(SlabLayout &s, char *base, const fb_problem *pr, const Derived &d
     size_t off = 0;
     auto take = [&](size_t n) { char *p = base ? base + off : nullptr; off += align_up(n); return p; };
     const size_t g = (size_t)d.W * d.H * (size_t)z_ext * sizeof(double);
-    s.vA = (double *)take(g);
-    s.wA = (double *)take(g);
+    // each pair is one block of 2 g bytes: two arrays of planes, or (q path) one array of interleaved (value, weight) nodes
+    s.vA = (double *)take(2 * g);
+    s.wA = base ? (double *)((char *)s.vA + g) : nullptr;
     s.off_vB = off;
-    s.vB = (double *)take(g);
-    s.off_wB = off;
-    s.wB = (double *)take(g);
+    s.vB = (double *)take(2 * g);
+    s.off_wB = s.off_vB + g;
+    s.wB = base ? (double *)((char *)s.vB + g) : nullptr;
+    s.off_out = off;
     s.out_ext = (float *)take(g / 2);
+    s.off_out64 = off;
     s.out64_ext = want64 ? (double *)take(g) : nullptr;
     const size_t R = (size_t)nsamples << pr->dim;
     memset(&s.inj, 0, sizeof s.inj);
@@ -2068,9 +2072,13 @@ int slab_carve(SlabLayout &s, char *base, const fb_problem *pr, const Derived &d
     s.inj.seg_node = (long long *)take(R * 8 + 8);
     s.inj.seg_base = (unsigned int *)take(R * 4 + 4);
     s.inj.seg_n = (unsigned int *)take(R * 4 + 4);
+    s.inj.link_next = (unsigned int *)take(R * 4 + 4);
     s.bytes = off;
     return FB_OK;
 }
+
+// the slab calls run the q kernels on interleaved nodes when the whole-grid path would (the in-place y sweep needs two passes)
+bool slab_interleaved(const fb_problem *pr, const Derived &d) { return use_sweepq(pr, d) && pr->num_iter >= 2; }
 
 int slab_check(const fb_problem *pr, Derived &d, long long z_begin, long long z_count, long long halo_lo, long long halo_hi)
 {
@@ -2092,6 +2100,28 @@ FB_EXPORT int64_t fb_slab_halo_planes(const fb_problem *prob)
     if (derive(prob, d) != FB_OK) return FB_EINVAL;
     if (prob->dim != 3) return fail(FB_EINVAL, "z-slab runs need dim == 3");
     return (int64_t)prob->num_iter * (d.ax[2].T + 1);
+}
+
+FB_EXPORT int fb_slab_result_offsets(const fb_problem *prob, int64_t nsamples, int64_t z_count, int64_t halo_lo, int64_t halo_hi,
+                                     int want_out64, int64_t *offset_out32, int64_t *offset_out64)
+{
+    Derived d;
+    int rc = derive(prob, d);
+    if (rc != FB_OK) return rc;
+    if (prob->dim != 3 || prob->nfields != 1) return fail(FB_EINVAL, "z-slab runs need dim == 3 and nfields == 1");
+    SlabLayout s;
+    slab_carve(s, nullptr, prob, d, nsamples, z_count + halo_lo + halo_hi, want_out64 != 0);
+    if (offset_out32) *offset_out32 = (int64_t)s.off_out;
+    if (offset_out64) *offset_out64 = want_out64 ? (int64_t)s.off_out64 : -1;
+    return FB_OK;
+}
+
+FB_EXPORT int fb_slab_interleaved(const fb_problem *prob)
+{
+    Derived d;
+    if (derive(prob, d) != FB_OK) return FB_EINVAL;
+    if (prob->dim != 3) return fail(FB_EINVAL, "z-slab runs need dim == 3");
+    return slab_interleaved(prob, d) ? 1 : 0;
 }
 
 FB_EXPORT int fb_slab_layout(const fb_problem *prob, int64_t nsamples, int64_t z_count, int64_t halo_lo, int64_t halo_hi,
@@ -2130,6 +2160,24 @@ int slab_phase1(const fb_problem *prob, int64_t z_begin, int64_t z_count, int64_
     const long long plane = d.W * d.H;
     // injection into the own planes, held in the middle of the extended A buffers
     Workspace w = s.inj;
+    if (slab_interleaved(prob, d)) {
+        // interleaved nodes: A2 / B2 are the 2 g byte blocks; the own planes' nodes are one contiguous run
+        double *a2 = s.vA + 2 * halo_lo * plane, *b2 = s.vB + 2 * halo_lo * plane;
+        w.vA = a2;
+        w.wA = a2 + z_count * plane;                  // second half of the own planes' block (run_inject zero-fills both halves)
+        w.vB = b2;
+        w.wB = b2 + z_count * plane;
+        if (do_inject && (rc = run_inject(prob, d, nsamples, nullptr, d_pts, d_val, w, st, z_begin, z_count, false, true)) != FB_OK)
+            return rc;
+        if (pc == 0) return FB_OK;
+        SweepCounters qctr{w.counters + 4, 0};
+        // x sweep A2 -> B2 (transposing), y sweep in place on B2, planes [pb, pb + pc)
+        rc = run_sweepq(1, prob->num_iter, d.ax[0], a2 + 2 * pb * plane, b2 + 2 * pb * plane, nullptr, nullptr, w.mm, d.csf, pc, d.W,
+                        d.H, st, qctr);
+        if (rc != FB_OK) return rc;
+        return run_sweepq(0, prob->num_iter, d.ax[1], b2 + 2 * pb * plane, b2 + 2 * pb * plane, nullptr, nullptr, w.mm, d.csf, pc, d.H,
+                          d.W, st, qctr);
+    }
     w.vA = s.vA + halo_lo * plane;
     w.wA = s.wA + halo_lo * plane;
     w.vB = s.vB + halo_lo * plane;
@@ -2176,30 +2224,52 @@ FB_EXPORT int fb_slab_sweeps_dev(const fb_problem *prob, int64_t z_begin, int64_
                        workspace_bytes, stream, false, plane_begin, plane_count);
 }
 
-FB_EXPORT int fb_slab_phase2_dev(const fb_problem *prob, int64_t z_begin, int64_t z_count, int64_t halo_lo, int64_t halo_hi,
-                                 int64_t nsamples, float *d_out, double *d_out64, void *d_workspace,
-                                 int64_t workspace_bytes, void *stream)
+namespace {
+int slab_phase2(const fb_problem *prob, int64_t z_begin, int64_t z_count, int64_t halo_lo, int64_t halo_hi, int64_t nsamples,
+                bool want64, float *d_out, double *d_out64, void *d_workspace, int64_t workspace_bytes, void *stream)
 {
     int rc = require_device();
     if (rc != FB_OK) return rc;
     Derived d;
     if ((rc = slab_check(prob, d, z_begin, z_count, halo_lo, halo_hi)) != FB_OK) return rc;
-    if (!d_out || !d_workspace) return fail(FB_EINVAL, "null device pointer");
+    if (!d_workspace) return fail(FB_EINVAL, "null device pointer");
     const long long z_ext = z_count + halo_lo + halo_hi;
     SlabLayout s;
-    slab_carve(s, (char *)d_workspace, prob, d, nsamples, z_ext, d_out64 != nullptr);
+    slab_carve(s, (char *)d_workspace, prob, d, nsamples, z_ext, want64);
     if ((long long)s.bytes > workspace_bytes) return fail(FB_ENOMEM, "workspace too small: need %zu bytes", s.bytes);
     cudaStream_t st = (cudaStream_t)stream;
     const long long plane = d.W * d.H;
     // fused z sweep + mask + divide + cast over the extended lines (A is free again: spare)
-    Pair cur{s.vB, s.wB}, spare{s.vA, s.wA};
     SweepCounters ctr{s.inj.counters + 4, 6};
-    rc = run_sweep(2, prob->num_iter, d.ax[2], cur, spare, s.out_ext, s.out64_ext, s.inj.mm, d.csf, 1, z_ext, plane, true, st, ctr);
+    if (slab_interleaved(prob, d)) {
+        rc = run_sweepq(2, prob->num_iter, d.ax[2], s.vB, nullptr, s.out_ext, s.out64_ext, s.inj.mm, d.csf, 1, z_ext, plane, st, ctr);
+    } else {
+        Pair cur{s.vB, s.wB}, spare{s.vA, s.wA};
+        rc = run_sweep(2, prob->num_iter, d.ax[2], cur, spare, s.out_ext, s.out64_ext, s.inj.mm, d.csf, 1, z_ext, plane, true, st, ctr);
+    }
     if (rc != FB_OK) return rc;
+    if (!d_out) return FB_OK;                        // the caller reads the own planes of the extended result in place
     CUDA_TRY(cudaMemcpyAsync(d_out, s.out_ext + halo_lo * plane, (size_t)plane * z_count * 4, cudaMemcpyDeviceToDevice, st));
     if (d_out64)
         CUDA_TRY(cudaMemcpyAsync(d_out64, s.out64_ext + halo_lo * plane, (size_t)plane * z_count * 8, cudaMemcpyDeviceToDevice, st));
     return FB_OK;
+}
+}  // namespace
+
+FB_EXPORT int fb_slab_phase2_dev(const fb_problem *prob, int64_t z_begin, int64_t z_count, int64_t halo_lo, int64_t halo_hi,
+                                 int64_t nsamples, float *d_out, double *d_out64, void *d_workspace,
+                                 int64_t workspace_bytes, void *stream)
+{
+    if (!d_out) return fail(FB_EINVAL, "null device pointer");
+    return slab_phase2(prob, z_begin, z_count, halo_lo, halo_hi, nsamples, d_out64 != nullptr, d_out, d_out64, d_workspace,
+                       workspace_bytes, stream);
+}
+
+FB_EXPORT int fb_slab_phase2_inplace_dev(const fb_problem *prob, int64_t z_begin, int64_t z_count, int64_t halo_lo, int64_t halo_hi,
+                                         int64_t nsamples, int want_out64, void *d_workspace, int64_t workspace_bytes, void *stream)
+{
+    return slab_phase2(prob, z_begin, z_count, halo_lo, halo_hi, nsamples, want_out64 != 0, nullptr, nullptr, d_workspace,
+                       workspace_bytes, stream);
 }
 
 // ---- S2 -------------------------------------------------------------------------------------------------

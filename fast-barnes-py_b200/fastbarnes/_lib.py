@@ -57,6 +57,7 @@ SIGNATURES = {
                                      ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                      ctypes.c_int64, ctypes.c_void_p]),
     'fb_slab_halo_planes': (ctypes.c_int64, [ctypes.POINTER(FbProblem)]),
+    'fb_slab_interleaved': (ctypes.c_int, [ctypes.POINTER(FbProblem)]),
     'fb_slab_layout': (ctypes.c_int, [ctypes.POINTER(FbProblem), ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
                                       ctypes.c_int64, ctypes.c_int, c_i64_p, c_i64_p, c_i64_p]),
     'fb_slab_phase1_dev': (ctypes.c_int, [ctypes.POINTER(FbProblem), ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
@@ -71,6 +72,11 @@ SIGNATURES = {
     'fb_slab_phase2_dev': (ctypes.c_int, [ctypes.POINTER(FbProblem), ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
                                           ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                           ctypes.c_int64, ctypes.c_void_p]),
+    'fb_slab_phase2_inplace_dev': (ctypes.c_int, [ctypes.POINTER(FbProblem), ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
+                                                  ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p,
+                                                  ctypes.c_int64, ctypes.c_void_p]),
+    'fb_slab_result_offsets': (ctypes.c_int, [ctypes.POINTER(FbProblem), ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
+                                              ctypes.c_int64, ctypes.c_int, c_i64_p, c_i64_p]),
     'fb_accumulate_lines_host': (ctypes.c_int, [c_double_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
                                                 ctypes.c_int64, ctypes.c_int, ctypes.c_double]),
     'fb_convolve_host': (ctypes.c_int, [ctypes.c_int, c_double_p, c_double_p, c_i64_p, c_i32_p, ctypes.c_int,

@@ -173,10 +173,29 @@ class BarnesSlab3D:
         with torch.cuda.device(self.device):
             self.workspace = torch.empty(nb.value, dtype=torch.uint8, device=self.device)
             nbytes = self.z_ext * H * W * 8
-            self.vB = self.workspace[ov.value:ov.value + nbytes].view(torch.float64).view(self.z_ext, H, W)
-            self.wB = self.workspace[ow.value:ow.value + nbytes].view(torch.float64).view(self.z_ext, H, W)
-            self.out = torch.empty((self.zc, H, W), dtype=torch.float32, device=self.device)
-            self.out64 = torch.empty((self.zc, H, W), dtype=torch.float64, device=self.device) if want_float64 else None
+            il = int(L.fb_slab_interleaved(self.prob))
+            if il < 0:
+                _lib.check(il)
+            self.interleaved = il == 1
+            if self.interleaved:
+                # one array of (value, weight) nodes; what the exchange moves are planes of it
+                self.nodes = self.workspace[ov.value:ov.value + 2 * nbytes].view(torch.float64).view(self.z_ext, H, W, 2)
+                self.vB, self.wB = self.nodes[..., 0], self.nodes[..., 1]
+                self.planes = (self.nodes,)
+            else:
+                self.vB = self.workspace[ov.value:ov.value + nbytes].view(torch.float64).view(self.z_ext, H, W)
+                self.wB = self.workspace[ow.value:ow.value + nbytes].view(torch.float64).view(self.z_ext, H, W)
+                self.planes = (self.vB, self.wB)
+            # the result stays where the z sweep writes it (the extended volume inside the workspace); `out` / `out64` are
+            # views of the own planes, valid until the next call
+            o32 = _lib.ctypes.c_int64()
+            o64 = _lib.ctypes.c_int64()
+            _lib.check(L.fb_slab_result_offsets(self.prob, self.nsamples, self.zc, self.halo_lo, self.halo_hi, int(want_float64),
+                                                _lib.ctypes.byref(o32), _lib.ctypes.byref(o64)))
+            a, b = self.halo_lo, self.halo_lo + self.zc
+            self.out = self.workspace[o32.value:o32.value + nbytes // 2].view(torch.float32).view(self.z_ext, H, W)[a:b]
+            self.out64 = (self.workspace[o64.value:o64.value + nbytes].view(torch.float64).view(self.z_ext, H, W)[a:b]
+                          if want_float64 else None)
             self.comm_stream = torch.cuda.Stream(device=self.device) if self.use_dist else None
         self.want64 = bool(want_float64)
         # planes of mine that other ranks need: [z0, z0 + lo_need) and [z1 - hi_need, z1)
@@ -237,7 +256,7 @@ class BarnesSlab3D:
         dist = self.dist
         ops = []
         for q, send, recv in self.transfers():
-            for buf in (self.vB, self.wB):
+            for buf in self.planes:
                 if send:
                     ops.append(dist.P2POp(dist.isend, buf[send[0] - self.ext0:send[1] - self.ext0], q, self.group))
                 if recv:
@@ -250,9 +269,8 @@ class BarnesSlab3D:
         torch, L, _lib = self.torch, self._lib.lib(), self._lib
         with torch.cuda.device(self.device):
             st = torch.cuda.current_stream().cuda_stream
-            _lib.check(L.fb_slab_phase2_dev(self.prob, self.z0, self.zc, self.halo_lo, self.halo_hi, self.nsamples,
-                                            self.out.data_ptr(), None if self.out64 is None else self.out64.data_ptr(),
-                                            self.workspace.data_ptr(), self.workspace.numel(), st))
+            _lib.check(L.fb_slab_phase2_inplace_dev(self.prob, self.z0, self.zc, self.halo_lo, self.halo_hi, self.nsamples,
+                                                    int(self.want64), self.workspace.data_ptr(), self.workspace.numel(), st))
         return self.out
 
     def __call__(self, pts, val):
@@ -308,7 +326,7 @@ def barnes_slabs_emulated(pts, val, sigma, x0, step, size, nslabs, num_iter=4, m
         for q, send, recv in s.transfers():
             if recv:
                 src = slabs[q]
-                for dst_buf, src_buf in ((s.vB, src.vB), (s.wB, src.wB)):
+                for dst_buf, src_buf in zip(s.planes, src.planes):
                     dst_buf[recv[0] - s.ext0:recv[1] - s.ext0].copy_(src_buf[recv[0] - src.ext0:recv[1] - src.ext0])
     outs = [s.phase2() for s in slabs]
     torch.cuda.synchronize()

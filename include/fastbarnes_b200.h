@@ -116,6 +116,10 @@ int fb_barnes_dev(const fb_problem *prob, int64_t nsamples, const int64_t *sampl
 /* ---- 3D z-slab decomposition (multi-GPU; no counterpart in the single-threaded reference) ---- */
 /* Halo planes a slab needs on each interior side: num_iter * (T_z + 1). */
 int64_t fb_slab_halo_planes(const fb_problem *prob);
+/* 1: the slab calls keep the extended B buffer as ONE array of interleaved (value, weight) double2 nodes
+ * [z_ext][H][W][2] starting at offset_vB (the second-generation sweep kernels); 0: two arrays of planes at offset_vB and
+ * offset_wB.  The halo exchange moves whole planes of whichever form is in use. */
+int fb_slab_interleaved(const fb_problem *prob);
 /* Workspace size of a slab of z_count own planes with halo_lo / halo_hi halo planes, and the byte
  * offsets of its extended B buffers (values, weights; [z_ext][y][x] float64) inside the workspace:
  * the caller writes the neighbours' planes into the halo parts between phase 1 and phase 2. */
@@ -141,6 +145,14 @@ int fb_slab_sweeps_dev(const fb_problem *prob, int64_t z_begin, int64_t z_count,
 int fb_slab_phase2_dev(const fb_problem *prob, int64_t z_begin, int64_t z_count, int64_t halo_lo, int64_t halo_hi,
                        int64_t nsamples, float *d_out, double *d_out64, void *d_workspace,
                        int64_t workspace_bytes, void *stream);
+
+/* The same, leaving the result where the z sweep writes it: the extended float32 volume [z_ext][y][x] at byte offset
+ * *offset_out32 of the workspace (and the fp64 quotient at *offset_out64, -1 if not requested); the own planes are planes
+ * halo_lo .. halo_lo + z_count - 1 of it.  Saves one device copy of the result per call. */
+int fb_slab_result_offsets(const fb_problem *prob, int64_t nsamples, int64_t z_count, int64_t halo_lo, int64_t halo_hi,
+                           int want_out64, int64_t *offset_out32, int64_t *offset_out64);
+int fb_slab_phase2_inplace_dev(const fb_problem *prob, int64_t z_begin, int64_t z_count, int64_t halo_lo, int64_t halo_hi,
+                               int64_t nsamples, int want_out64, void *d_workspace, int64_t workspace_bytes, void *stream);
 
 /* ---- stages (private-but-tested functions of the reference) -------------------------------- */
 /* interpolation.py:485-533 _accumulate_tail_array (alpha) / :729-772 _accumulate_array

@@ -482,7 +482,8 @@ def test_1d_exact_2e22_points_is_fast(fb, orc):
     assert dt < 0.060, dt
 
 
-def test_z_slab_decomposition_single_gpu(fb):
+@pytest.mark.parametrize('sig', [[0.9, 0.8, 0.7], [1.3, 1.2, 1.1]], ids=['planes_T2', 'interleaved_T3'])
+def test_z_slab_decomposition_single_gpu(fb, sig):
     """ 3D z-slabs, emulated on one GPU: own planes are injected and x/y-swept per slab (boundary planes
     first, as the multi-GPU run does to overlap the exchange), halo planes copied between the slabs, fused z sweep per slab.
     Tolerance: the x/y stages are bit-identical; the z sweep restarts its accumulator at the halo edge, so the fp64
@@ -490,14 +491,17 @@ def test_z_slab_decomposition_single_gpu(fb):
     range, not against the quotient itself, because a relative bound is meaningless where the field crosses zero
     (zero-centred values are one of the cases) -- NaN mask identical, float32 equal on > 99.9 % of the points and never
     off by more than 1 ulp where |field| > 1e-3 * range.  Slabs thinner than the halo (16 slabs of 7-8 planes, halo 12)
-    take their halo planes from several ranks. """
+    take their halo planes from several ranks.  The two kernel widths run the two forms of the slab buffers: planes of
+    values and of weights (T=2: first-generation kernels) and interleaved nodes (T=3: q kernels). """
     from fastbarnes import distributed
     rng = np.random.default_rng(8)
     size = (96, 80, 120)
     N = 4000
     pts = rng.uniform(0.0, 1.0, (N, 3)) * (np.asarray(size) - 1) * 0.25
     pts[:200] = pts[200:400]
-    sig = [0.9, 0.8, 0.7]
+    probe = distributed.BarnesSlab3D(sig, [0.0, 0.0, 0.0], 0.25, size, N, num_iter=4, nslabs=1, slab=0)
+    assert probe.interleaved == (sig[0] > 1.0)
+    del probe
     for centre in (280.0, 0.0):
         val = rng.normal(centre, 7.0, N)
         vrange = float(val.max() - val.min())
