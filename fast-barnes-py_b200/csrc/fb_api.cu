@@ -29,14 +29,8 @@ namespace {
 thread_local std::string g_err;
 std::atomic<long long> g_launches{0};
 std::atomic<int> g_profiling{0};
-// tensor-memory use of the fp64 sweeps: 0 none, non-zero (default) the hybrid kernel for launches with enough work items
-std::atomic<int> g_tmem{3};
-// fp64 injection as interleaved (value, weight) nodes when the hybrid x sweep consumes it: 0 off, non-zero (default) on
-std::atomic<int> g_interleaved{1};
 // interleaved form: records linked into per-node lists (two passes over the samples) instead of count / allocate / place
 std::atomic<int> g_inject_lists{1};
-std::atomic<int> g_three_warp{1};   // tuning switch: three-stage sweep kernels on/off
-std::atomic<int> g_two_warp{1};     // tuning switch (fb_set_option): two-warp sweep kernels on/off
 // second-generation sweep kernels (fb_sweepq.cuh): 0 off, non-zero (default) on for 2D / 3D fp64 grids they cover
 std::atomic<int> g_sweepq{1};
 std::atomic<int> g_q_nst{3};        // staging slots (chunks of rows in flight) per warp
@@ -159,276 +153,6 @@ size_t sweep_smem_bytes(int npass, int mode, int D)
     size_t b = (size_t)nr * sweep_ring_depth(D) * 32 * sizeof(double);
     if (mode == 1) b += (size_t)FB_TILE_K * FB_TILE_PITCH * sizeof(double);
     return b;
-}
-
-// two-warp kernel: split of npass into (NA, NB); B gets the smaller half except that the
-// finalising sweep (MODE 2, expensive division in warp B) gives B a single pass when npass >= 3
-std::atomic<int> g_na_shift{0};     // tuning: moves passes between the two warps of fb_sweep2_kernel
-inline int sweep2_na(int npass, int mode)
-{
-    if (mode == 2) return npass;
-    // warp A also does the global loads and prefetches: it gets the smaller share (measured)
-    int na = (npass - 1) / 2 + g_na_shift.load();
-    if (na < 1) na = 1;
-    if (na > npass - 1) na = npass - 1;
-    return na;
-}
-
-size_t sweep2_smem_bytes(int npass, int mode, int D)
-{
-    const int U = FB_SWEEP_U;
-    const int R = sweep_ring_depth(D);
-    const int na = sweep2_na(npass, mode), nb = npass - na;
-    const int R2 = nb > 0 ? (D + 2 * U + U - 1) / U * U : 2 * U;
-    const int nrings = (na - 1) + (nb > 0 ? nb - 1 : 0);
-    size_t b = ((size_t)nrings * R + R2) * 32 * sizeof(double);
-    if (mode == 1) b += (size_t)FB_TILE_K * FB_TILE_PITCH * sizeof(double);
-    return b;
-}
-
-template <int NA, int NB, int MODE>
-int launch_sweep2_t(const FbSweep &p, size_t smem, cudaStream_t st)
-{
-    static thread_local size_t configured[16] = {0};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (smem > 48 * 1024 && configured[dev & 15] < smem) {
-        CUDA_TRY(cudaFuncSetAttribute(fb_sweep2_kernel<NA, NB, MODE, FB_SWEEP_U>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)kSmemLimit));
-        CUDA_TRY(cudaFuncSetAttribute(fb_sweep2_kernel<NA, NB, MODE, FB_SWEEP_U>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                      cudaSharedmemCarveoutMaxShared));
-        configured[dev & 15] = kSmemLimit;
-    }
-    const long long nitems = p.n_outer * p.n_groups;
-    if (nitems <= 0) return FB_OK;
-    static thread_local int occ[16] = {0};
-    static thread_local size_t occ_smem[16] = {0};
-    if (occ[dev & 15] == 0 || occ_smem[dev & 15] != smem) {
-        int nb = 0;
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fb_sweep2_kernel<NA, NB, MODE, FB_SWEEP_U>, 64, smem));
-        occ[dev & 15] = nb > 0 ? nb : 1;
-        occ_smem[dev & 15] = smem;
-    }
-    long long grid = (long long)occ[dev & 15] * sm_count(dev);
-    if (grid > nitems) grid = nitems;
-    CUDA_TRY(cudaMemsetAsync(p.work_counter, 0, sizeof(unsigned long long), st));
-    fb_sweep2_kernel<NA, NB, MODE, FB_SWEEP_U><<<(unsigned)grid, 64, smem, st>>>(p);
-    LAUNCH_CHECK();
-    return FB_OK;
-}
-
-template <int MODE>
-int launch_sweep2_m(int npass, const FbSweep &p, size_t smem, cudaStream_t st)
-{
-#ifdef FBQ_LAB
-    (void)npass;
-    return fail(FB_EKERNEL, "lab build: kernel family compiled out");
-#else
-    const int na = sweep2_na(npass, MODE);
-    if constexpr (MODE == 2) {
-        switch (npass) {
-        case 1: return launch_sweep2_t<1, 0, MODE>(p, smem, st);
-        case 2: return launch_sweep2_t<2, 0, MODE>(p, smem, st);
-        case 3: return launch_sweep2_t<3, 0, MODE>(p, smem, st);
-        case 4: return launch_sweep2_t<4, 0, MODE>(p, smem, st);
-        case 5: return launch_sweep2_t<5, 0, MODE>(p, smem, st);
-        case 6: return launch_sweep2_t<6, 0, MODE>(p, smem, st);
-        }
-    } else {
-        switch (npass * 10 + na) {
-        case 21: return launch_sweep2_t<1, 1, MODE>(p, smem, st);
-        case 31: return launch_sweep2_t<1, 2, MODE>(p, smem, st);
-        case 32: return launch_sweep2_t<2, 1, MODE>(p, smem, st);
-        case 41: return launch_sweep2_t<1, 3, MODE>(p, smem, st);
-        case 42: return launch_sweep2_t<2, 2, MODE>(p, smem, st);
-        case 52: return launch_sweep2_t<2, 3, MODE>(p, smem, st);
-        case 53: return launch_sweep2_t<3, 2, MODE>(p, smem, st);
-        case 62: return launch_sweep2_t<2, 4, MODE>(p, smem, st);
-        case 63: return launch_sweep2_t<3, 3, MODE>(p, smem, st);
-        }
-    }
-    return fail(FB_EINVAL, "unsupported pass split: %d/%d", npass, na);
-#endif
-}
-
-// three-warp kernel: stage split (S0, S1, S2) of npass passes
-inline void sweep3_split(int npass, int mode, int &s0, int &s1, int &s2)
-{
-    if (mode == 2) {            // last stage only finalises (divisions)
-        s2 = 0;
-        s1 = npass / 2;
-        s0 = npass - s1;
-    } else {                    // first stage also loads: give it the smaller share
-        s0 = npass / 3;
-        if (s0 < 1) s0 = 1;
-        s2 = (npass - s0) / 2;
-        s1 = npass - s0 - s2;
-    }
-}
-
-size_t sweep3_smem_bytes(int npass, int mode, int D)
-{
-    const int U = FB_SWEEP_U;
-    const int R = sweep_ring_depth(D);
-    int s0, s1, s2;
-    sweep3_split(npass, mode, s0, s1, s2);
-    const int H0 = (D + 2 * U + U - 1) / U * U;
-    const int H1 = s2 > 0 ? H0 : 2 * U;
-    const int nrings = (s0 - 1) + (s1 - 1) + (s2 > 0 ? s2 - 1 : 0);
-    size_t b = ((size_t)nrings * R + H0 + H1) * 32 * sizeof(double);
-    if (mode == 1) b += (size_t)FB_TILE3_K * FB_TILE3_PITCH * sizeof(double);
-    return b;
-}
-
-template <int S0, int S1, int S2, int MODE>
-int launch_sweep3_t(const FbSweep &p, size_t smem, cudaStream_t st)
-{
-    static thread_local size_t configured[16] = {0};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (smem > 48 * 1024 && configured[dev & 15] < smem) {
-        CUDA_TRY(cudaFuncSetAttribute(fb_sweep3_kernel<S0, S1, S2, MODE, FB_SWEEP_U>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)kSmemLimit));
-        CUDA_TRY(cudaFuncSetAttribute(fb_sweep3_kernel<S0, S1, S2, MODE, FB_SWEEP_U>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                      cudaSharedmemCarveoutMaxShared));
-        configured[dev & 15] = kSmemLimit;
-    }
-    const long long nitems = p.n_outer * p.n_groups;
-    if (nitems <= 0) return FB_OK;
-    static thread_local int occ[16] = {0};
-    static thread_local size_t occ_smem[16] = {0};
-    if (occ[dev & 15] == 0 || occ_smem[dev & 15] != smem) {
-        int nb = 0;
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fb_sweep3_kernel<S0, S1, S2, MODE, FB_SWEEP_U>, 96, smem));
-        occ[dev & 15] = nb > 0 ? nb : 1;
-        occ_smem[dev & 15] = smem;
-    }
-    long long grid = (long long)occ[dev & 15] * sm_count(dev);
-    if (grid > nitems) grid = nitems;
-    CUDA_TRY(cudaMemsetAsync(p.work_counter, 0, sizeof(unsigned long long), st));
-    fb_sweep3_kernel<S0, S1, S2, MODE, FB_SWEEP_U><<<(unsigned)grid, 96, smem, st>>>(p);
-    LAUNCH_CHECK();
-    return FB_OK;
-}
-
-template <int MODE>
-int launch_sweep3_m(int npass, const FbSweep &p, size_t smem, cudaStream_t st)
-{
-#ifdef FBQ_LAB
-    (void)npass;
-    return fail(FB_EKERNEL, "lab build: kernel family compiled out");
-#else
-    if constexpr (MODE == 2) {
-        switch (npass) {
-        case 2: return launch_sweep3_t<1, 1, 0, MODE>(p, smem, st);
-        case 3: return launch_sweep3_t<2, 1, 0, MODE>(p, smem, st);
-        case 4: return launch_sweep3_t<2, 2, 0, MODE>(p, smem, st);
-        case 5: return launch_sweep3_t<3, 2, 0, MODE>(p, smem, st);
-        case 6: return launch_sweep3_t<3, 3, 0, MODE>(p, smem, st);
-        }
-    } else {
-        switch (npass) {
-        case 3: return launch_sweep3_t<1, 1, 1, MODE>(p, smem, st);
-        case 4: return launch_sweep3_t<1, 2, 1, MODE>(p, smem, st);
-        case 5: return launch_sweep3_t<1, 2, 2, MODE>(p, smem, st);
-        case 6: return launch_sweep3_t<2, 2, 2, MODE>(p, smem, st);
-        }
-    }
-    return fail(FB_EINVAL, "unsupported three-stage split of %d passes", npass);
-#endif
-}
-
-// hybrid kernel: two two-warp pipelines per CTA, private rings in tensor memory
-inline void sweeph_split(int npass, int &na, int &nb) { na = npass / 2; nb = npass - na; }
-inline int sweeph_tmem_cols(int npass, int D)
-{
-    int na, nb;
-    sweeph_split(npass, na, nb);
-    const int rings = (nb - 1) > (na - 1) ? (nb - 1) : (na - 1);
-    int need = rings * sweep_ring_depth(D) * 2, cols = 32;
-    while (cols < need) cols *= 2;
-    return cols;
-}
-size_t sweeph_smem_bytes(int mode, int D)
-{
-    const int U = FB_SWEEP_U;
-    const int R2 = (D + 2 * U + U - 1) / U * U;
-    size_t b = (size_t)R2 * 32 * sizeof(double);
-    if (mode == 1) b += (size_t)FB_TILE_K * FB_TILE_PITCH * sizeof(double);
-    return 2 * b;
-}
-inline bool sweeph_fits(int npass, int D)
-{
-    return npass >= 2 && npass <= 6 && sweep_chunk(D) == FB_SWEEP_U && sweeph_tmem_cols(npass, D) <= 128 &&
-           2 * (sweeph_smem_bytes(1, D) + 1024) <= kSmemPerSM;      // at least two CTAs (four pipelines) per SM
-}
-
-template <int NA, int NB, int MODE, int ES>
-int launch_sweeph_es(FbSweep p, int npass, cudaStream_t st)
-{
-    static thread_local size_t configured[16] = {0};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    const size_t smem = sweeph_smem_bytes(MODE, p.D);
-    if (smem > 40 * 1024 && configured[dev & 15] < smem) {     // static shared memory counts too
-        CUDA_TRY(cudaFuncSetAttribute(fb_sweeph_kernel<NA, NB, MODE, FB_SWEEP_U, ES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)kSmemLimit));
-        CUDA_TRY(cudaFuncSetAttribute(fb_sweeph_kernel<NA, NB, MODE, FB_SWEEP_U, ES>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                      cudaSharedmemCarveoutMaxShared));
-        configured[dev & 15] = kSmemLimit;
-    }
-    const long long nitems = p.n_outer * p.n_groups;
-    if (nitems <= 0) return FB_OK;
-    p.tmem_cols = sweeph_tmem_cols(npass, p.D);
-    // CTAs per SM: 128 registers x 128 threads (launch bounds) -> 4 by registers; shared memory and
-    // tensor-memory columns bound it further (the occupancy API reports 0 for this kernel)
-    int occ_est = 4;
-    if ((int)(kSmemPerSM / (smem + 1024)) < occ_est) occ_est = (int)(kSmemPerSM / (smem + 1024));
-    if (occ_est < 1) occ_est = 1;
-    int per_sm = occ_est;
-    if (per_sm * p.tmem_cols > 512) per_sm = 512 / p.tmem_cols;      // tensor-memory columns bound the CTAs per SM
-    long long grid = (long long)per_sm * sm_count(dev);
-    if (grid > (nitems + 1) / 2) grid = (nitems + 1) / 2;
-    if (getenv("FB_DEBUG")) fprintf(stderr, "[fb] sweeph<%d,%d,%d> smem %zu occ %d tmem_cols %d per_sm %d grid %lld items %lld\n", NA, NB, MODE, smem, occ_est, p.tmem_cols, per_sm, grid, nitems);
-    CUDA_TRY(cudaMemsetAsync(p.work_counter, 0, sizeof(unsigned long long), st));
-    fb_sweeph_kernel<NA, NB, MODE, FB_SWEEP_U, ES><<<(unsigned)grid, 128, smem, st>>>(p);
-    LAUNCH_CHECK();
-    return FB_OK;
-}
-
-template <int NA, int NB, int MODE>
-int launch_sweeph_t(const FbSweep &p, int npass, cudaStream_t st)
-{
-    if constexpr (MODE == 1) {
-        if (p.in_es == 2) return launch_sweeph_es<NA, NB, 1, 2>(p, npass, st);
-    }
-    if (p.in_es != 1) return fail(FB_EINVAL, "internal: interleaved input is read by the transposing sweep only");
-    return launch_sweeph_es<NA, NB, MODE, 1>(p, npass, st);
-}
-
-template <int MODE>
-int launch_sweeph_m(int npass, const FbSweep &p, cudaStream_t st)
-{
-#ifdef FBQ_LAB
-    (void)npass;
-    return fail(FB_EKERNEL, "lab build: kernel family compiled out");
-#else
-    switch (npass) {
-    case 2: return launch_sweeph_t<1, 1, MODE>(p, npass, st);
-    case 3: return launch_sweeph_t<1, 2, MODE>(p, npass, st);
-    case 4: return launch_sweeph_t<2, 2, MODE>(p, npass, st);
-    case 5: return launch_sweeph_t<2, 3, MODE>(p, npass, st);
-    case 6: return launch_sweeph_t<3, 3, MODE>(p, npass, st);
-    }
-    return fail(FB_EINVAL, "unsupported number of fused passes: %d", npass);
-#endif
-}
-
-int launch_sweeph(int m, int npass, const FbSweep &p, cudaStream_t st)
-{
-    if (m == 0) return launch_sweeph_m<0>(npass, p, st);
-    if (m == 1) return launch_sweeph_m<1>(npass, p, st);
-    return launch_sweeph_m<2>(npass, p, st);
 }
 
 // ---- second-generation sweeps: fb_sweepq_kernel ------------------------------------------------------------------
@@ -871,19 +595,12 @@ inline int sweep_fmax(int mode, int D)
         if (sweep_smem_bytes(f, mode, D) <= kSmemLimit) fmax = f;
     return fmax;
 }
-inline bool sweep_is_single_hybrid(int mode, int num_iter, int T, long long n_outer, long long n_inner)
-{
-    const int D = 2 * T + 2;
-    const int fmax = sweep_fmax(mode, D);
-    if ((num_iter + fmax - 1) / fmax != 1) return false;
-    return g_tmem.load() != 0 && sweeph_fits(num_iter, D) && n_outer * ((n_inner + 15) / 16) >= 8LL * sm_count_current();
-}
-
-// interleaved_in: `cur` is the injection grid in its interleaved form (cur.v = first value, cur.w = cur.v + 1);
-// only valid when sweep_is_single_hybrid() holds for this sweep.
+// first-generation sweep of one axis on planes of values and of weights (fb_sweep_kernel): 1D lines, kernels of fewer
+// than 8 elements, kernels whose rings do not fit on chip (the launch is then split into groups of passes), and the
+// cross-check of the q path in the tests
 int run_sweep(int mode, int num_iter, AxisParams ax, Pair &cur, Pair &spare, float *out32, double *out64,
               const unsigned long long *mm, double csf, long long n_outer, long long L, long long n_inner,
-              bool has_w, cudaStream_t st, SweepCounters &ctr, bool interleaved_in = false)
+              bool has_w, cudaStream_t st, SweepCounters &ctr)
 {
     FbSweep p{};
     p.n_outer = n_outer;
@@ -901,11 +618,8 @@ int run_sweep(int mode, int num_iter, AxisParams ax, Pair &cur, Pair &spare, flo
     p.out64 = out64;
     if (L > 2147483647LL - 8 * (long long)(ax.T + 1) - 64) return fail(FB_EINVAL, "line too long: %lld", L);
 
-    p.in_es = 1;
     const int fmax = sweep_fmax(mode, p.D);
     const int nlaunch = (num_iter + fmax - 1) / fmax;
-    if (interleaved_in && !(has_w && sweep_is_single_hybrid(mode, num_iter, ax.T, n_outer, n_inner)))
-        return fail(FB_EINVAL, "internal: interleaved input needs the single-launch hybrid sweep");
     int remaining = num_iter;
     for (int l = 0; l < nlaunch; ++l) {
         const int np = (remaining + (nlaunch - l) - 1) / (nlaunch - l);
@@ -927,35 +641,7 @@ int run_sweep(int mode, int num_iter, AxisParams ax, Pair &cur, Pair &spare, flo
             p.out_w = spare.w;
         }
         int rc = FB_OK;
-        if (g_tmem.load() != 0 && sweeph_fits(np, p.D) && p.n_outer * p.n_groups >= 8LL * sm_count_current()) {
-            // hybrid: two-warp pipelines, private rings in tensor memory, 8 pipelines per SM
-            p.in_es = interleaved_in ? 2 : 1;
-            rc = launch_sweeph(m, np, p, st);
-            if (rc != FB_OK) return rc;
-            if (m != 2 && !in_place) { Pair t2 = cur; cur = spare; spare = t2; }
-            continue;
-        }
-        // two warps per 16 lines when the launch fuses >= 2 passes (general chunk length only)
-        const bool two_warps = g_two_warp.load() && (np >= 2 || m == 2) && sweep_chunk(p.D) == FB_SWEEP_U &&
-                               sweep2_smem_bytes(np, m, p.D) <= kSmemLimit;
-        // three stages when the launch has enough passes and the extra hand-over ring still lets
-        // the same number of CTAs fit on an SM
-        const bool three_warps = two_warps && (m == 2 ? g_three_warp.load() != 0 : g_three_warp.load() > 1) &&
-                                 (m == 2 ? np >= 2 : np >= 3) &&
-                                 sweep3_smem_bytes(np, m, p.D) <= kSmemLimit &&
-                                 (kSmemPerSM / (sweep3_smem_bytes(np, m, p.D) + 1024)) >=
-                                     (kSmemPerSM / (sweep2_smem_bytes(np, m, p.D) + 1024));
-        if (three_warps) {
-            const size_t smem = sweep3_smem_bytes(np, m, p.D);
-            if (m == 0) rc = launch_sweep3_m<0>(np, p, smem, st);
-            else if (m == 1) rc = launch_sweep3_m<1>(np, p, smem, st);
-            else rc = launch_sweep3_m<2>(np, p, smem, st);
-        } else if (two_warps) {
-            const size_t smem = sweep2_smem_bytes(np, m, p.D);
-            if (m == 0) rc = launch_sweep2_m<0>(np, p, smem, st);
-            else if (m == 1) rc = launch_sweep2_m<1>(np, p, smem, st);
-            else rc = launch_sweep2_m<2>(np, p, smem, st);
-        } else {
+        {
             const size_t smem = sweep_smem_bytes(np, m, p.D);
             if (smem > kSmemLimit) return fail(FB_EKERNEL, "ring storage does not fit: T=%d passes=%d", ax.T, np);
             if (m == 0) rc = launch_sweep_m<0>(np, p, smem, st);
@@ -1283,12 +969,8 @@ int run_inject_sparse(const fb_problem *pr, const Derived &d, long long nsamples
     return FB_OK;
 }
 
-bool inject_interleaved(const fb_problem *pr, const Derived &d)
-{
-    if (use_sweepq(pr, d)) return true;
-    if (pr->dim < 2 || (pr->flags & FB_FLAG_FP32) || g_interleaved.load() == 0) return false;
-    return sweep_is_single_hybrid(1, pr->num_iter, d.ax[0].T, (long long)pr->nfields * d.Dz, d.H);
-}
+// the injection writes interleaved (value, weight) nodes exactly when the q path consumes them
+bool inject_interleaved(const fb_problem *pr, const Derived &d) { return use_sweepq(pr, d); }
 
 // ---- 1D grids: the bit-exact walk of a long line (fb_line1d_kernel) ------------------------------------------------
 struct Line1DPlan { bool ok; int DL, RL; size_t smem; };
@@ -1435,13 +1117,8 @@ int run_sweeps(const fb_problem *pr, const Derived &d, Workspace &w, float *d_ou
         return prof_mark(5, st);
     }
     // x sweep: A layout [..][x][y] -> natural layout [..][y][x]
-    if (inject_interleaved(pr, d)) cur = Pair{w.vA, w.vA + 1};       // interleaved (value, weight) nodes
-    rc = run_sweep(1, n, d.ax[0], cur, spare, nullptr, nullptr, w.mm, d.csf, nf * d.Dz, d.W, d.H, true, st, ctr,
-                   inject_interleaved(pr, d));
+    rc = run_sweep(1, n, d.ax[0], cur, spare, nullptr, nullptr, w.mm, d.csf, nf * d.Dz, d.W, d.H, true, st, ctr);
     if (rc != FB_OK) return rc;
-    // the A block is free now; later launches that are not in place write PLANES into it (the interleaved alias
-    // {vA, vA + 1} the x sweep read must not survive as an output pair)
-    spare = (cur.v == w.vB) ? Pair{w.vA, w.wA} : Pair{w.vB, w.wB};
     if ((rc = prof_mark(3, st)) != FB_OK) return rc;
     if (pr->dim == 2) {
         rc = run_sweep(2, n, d.ax[1], cur, spare, d_out, d_out64, w.mm, d.csf, nf, d.H, d.W, true, st, ctr);
@@ -2501,11 +2178,6 @@ FB_EXPORT int64_t fb_kernel_launch_count(void) { return g_launches.load(); }
 FB_EXPORT int fb_set_option(const char *name, int value)
 {
     if (!name) return fail(FB_EINVAL, "null option name");
-    if (!strcmp(name, "two_warp_sweeps")) { g_two_warp.store(value ? 1 : 0); return FB_OK; }
-    if (!strcmp(name, "three_warp_sweeps")) { g_three_warp.store(value ? 1 : 0); return FB_OK; }
-    if (!strcmp(name, "sweep2_na_shift")) { g_na_shift.store(value); return FB_OK; }
-    if (!strcmp(name, "tmem_sweeps")) { g_tmem.store(value); return FB_OK; }
-    if (!strcmp(name, "interleaved_inject")) { g_interleaved.store(value); return FB_OK; }
     if (!strcmp(name, "inject_lists")) { g_inject_lists.store(value); return FB_OK; }
     if (!strcmp(name, "host_chunk_fields")) { g_host_chunk_fields.store(value); return FB_OK; }
     if (!strcmp(name, "sweepq")) { g_sweepq.store(value); return FB_OK; }

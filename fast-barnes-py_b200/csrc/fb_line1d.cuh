@@ -34,7 +34,9 @@ struct FbLine1D {
     double alpha, csf;
 };
 
-__device__ __forceinline__ void fbl_bar() { asm volatile("bar.sync 1, 64;" ::: "memory"); }
+// the non-aligned form: the lanes of the feeding warp arrive from lane-dependent branches (loads past the end of the line,
+// rows outside it) and need not have reconverged (compute-sanitizer synccheck flags `bar.sync` there)
+__device__ __forceinline__ void fbl_bar() { asm volatile("barrier.sync 1, 64;" ::: "memory"); }
 
 template <int NPASS, int MODE>
 __global__ void __launch_bounds__(64, 1)

@@ -177,14 +177,6 @@ def lib():
             fn.restype = res
             fn.argtypes = args
         # tuning switches from the environment (results are bit-identical either way)
-        if os.environ.get('FB_TWO_WARP_SWEEPS') is not None:
-            L.fb_set_option(b'two_warp_sweeps', int(os.environ['FB_TWO_WARP_SWEEPS']))
-        if os.environ.get('FB_THREE_WARP_SWEEPS') is not None:
-            L.fb_set_option(b'three_warp_sweeps', int(os.environ['FB_THREE_WARP_SWEEPS']))
-        if os.environ.get('FB_SWEEP2_NA_SHIFT') is not None:
-            L.fb_set_option(b'sweep2_na_shift', int(os.environ['FB_SWEEP2_NA_SHIFT']))
-        if os.environ.get('FB_TMEM_SWEEPS') is not None:
-            L.fb_set_option(b'tmem_sweeps', int(os.environ['FB_TMEM_SWEEPS']))
         if os.environ.get('FB_HOST_CHUNK_FIELDS') is not None:
             L.fb_set_option(b'host_chunk_fields', int(os.environ['FB_HOST_CHUNK_FIELDS']))
         for env, opt in (('FB_SWEEPQ', b'sweepq'), ('FB_SWEEPQ_STAGES', b'sweepq_stages'),

@@ -249,7 +249,7 @@ def test_batched_equals_singles(fb):
 
 def test_chunked_host_pipeline_and_kernel_variants(fb):
     """ tuning switches never change bits: multi-stream chunking of the host entry (ragged fields,
-    partial last chunk) and one-warp vs two-warp sweep kernels """
+    partial last chunk) and q kernels vs first-generation sweep kernels """
     from fastbarnes import _lib
     L = _lib.lib()
     rng = np.random.default_rng(21)
@@ -268,11 +268,11 @@ def test_chunked_host_pipeline_and_kernel_variants(fb):
         b = fb.barnes_batched(p3, v3, 1.2, [0.0, 0.0], 0.1, size, num_iter=5)
         _lib.check(L.fb_set_option(b'host_chunk_fields', 4))
         b_ref = fb.barnes_batched(p3, v3, 1.2, [0.0, 0.0], 0.1, size, num_iter=5)
-        _lib.check(L.fb_set_option(b'two_warp_sweeps', 0))
+        _lib.check(L.fb_set_option(b'sweepq', 0))
         c = fb.barnes_batched(pts, val, 1.2, [0.0, 0.0], 0.1, size, sample_offsets=offs, num_iter=4)
     finally:
         L.fb_set_option(b'host_chunk_fields', 4)
-        L.fb_set_option(b'two_warp_sweeps', 1)
+        L.fb_set_option(b'sweepq', 1)
     assert bits_equal(a, ref) and bits_equal(c, ref) and bits_equal(b, b_ref)
     for i in range(len(counts)):
         single = fb.barnes(pts[offs[i]:offs[i + 1]], val[offs[i]:offs[i + 1]], 1.2, [0.0, 0.0], 0.1, size, num_iter=4)
@@ -772,11 +772,11 @@ def test_fp32_path_shapes_batches_3d(fb):
 
 
 # ---------------------------------------------------------------------------------------------
-# large batches: the hybrid sweep kernels (two-warp pipelines, rings in tensor memory) take over at >= 8 work
-# items per SM, i.e. only for batches like bench.py's; check them against the oracle and the shared-memory kernels
+# large batches (device-resident, like bench.py's): the q kernels against the oracle and against the first-generation
+# shared-memory kernel
 
 @pytest.mark.parametrize('ratio,iters', [(8, (2, 3, 4, 5, 6)), (32, (4,))])
-def test_large_batch_hybrid_kernels(fb, orc, ratio, iters):
+def test_large_batch_kernels(fb, orc, ratio, iters):
     """ device-resident batches (the host entry point works in chunks of 4 fields and never gets there) """
     torch = pytest.importorskip('torch')
     from fastbarnes import _lib
@@ -803,10 +803,10 @@ def test_large_batch_hybrid_kernels(fb, orc, ratio, iters):
         for method in (('optimized_convolution', 'convolution') if n == 4 else ('optimized_convolution',)):
             out, _ = run(method, n)
             try:
-                _lib.check(L.fb_set_option(b'tmem_sweeps', 0))
+                _lib.check(L.fb_set_option(b'sweepq', 0))
                 smem, _ = run(method, n)
             finally:
-                L.fb_set_option(b'tmem_sweeps', 1)
+                L.fb_set_option(b'sweepq', 1)
             assert bits_equal(out, smem), (n, method)
             for i in (0, 17, F - 1):
                 ref = orc.barnes(pts[i], val[i], 1.0, [0.0, 0.0], step, size, method=method, num_iter=n, nthreads=4)
@@ -817,8 +817,27 @@ def test_large_batch_hybrid_kernels(fb, orc, ratio, iters):
     assert fp32_close(a, b, float(val.max() - val.min()))
 
 
+def test_bench_shape_against_oracle(fb, orc):
+    """ The exact workload of bench.py (BASELINE configs[1]): 2400x1200 grid at 1/32 degree, 50000 samples
+    per field, sigma 1 degree, 4 passes, the samples bench.make_fields draws.  One field through the host API and one
+    64-field sub-batch device-resident (what one timed launch of the bench processes): fields 0, 31 and 63 bit for bit
+    against the oracle. """
+    torch = pytest.importorskip('torch')
+    import bench
+    pts, val = bench.make_fields(0, bench.SUB_FIELDS)
+    refs = {i: orc.barnes(pts[i], val[i], bench.SIGMA, bench.X0, bench.STEP, bench.SIZE, num_iter=bench.NUM_ITER, nthreads=8)
+            for i in (0, 31, bench.SUB_FIELDS - 1)}
+    one = fb.barnes(pts[0], val[0], bench.SIGMA, bench.X0, bench.STEP, bench.SIZE, num_iter=bench.NUM_ITER)
+    assert one.shape == (1200, 2400) and bits_equal(one, refs[0])
+    F, N = bench.SUB_FIELDS, bench.N_PER_FIELD
+    plan = fb.BarnesDevice(2, bench.SIGMA, bench.X0, bench.STEP, bench.SIZE, nfields=F, nsamples=F * N, num_iter=bench.NUM_ITER)
+    out = plan(torch.from_numpy(pts.reshape(F * N, 2)).cuda(), torch.from_numpy(val.reshape(F * N)).cuda())
+    for i, ref in refs.items():
+        assert bits_equal(out[i].cpu().numpy(), ref), i
+
+
 def test_injection_lists_vs_segments(fb, orc):
-    """ Interleaved fp64 nodes (the form the hybrid x sweep reads): the two-pass injection that links the
+    """ Interleaved fp64 nodes (the form the q sweeps read): the two-pass injection that links the
     records of a node into a list against the three-pass count / allocate / place version and the oracle,
     bit for bit -- random samples, repeated locations (lists of 25 records: heap sort; of 2: insertion sort)
     and fields with every sample in a single cell or at a single location (lists of 1500 records). """
@@ -845,11 +864,11 @@ def test_injection_lists_vs_segments(fb, orc):
         _lib.check(L.fb_set_option(b'inject_lists', 0))
         seg = plan(d_pts, d_val).cpu().numpy()
         seg64 = plan.out64.cpu().numpy()
-        _lib.check(L.fb_set_option(b'interleaved_inject', 0))
+        _lib.check(L.fb_set_option(b'sweepq', 0))         # planes of values / weights, first-generation sweeps
         planes = plan(d_pts, d_val).cpu().numpy()
     finally:
         L.fb_set_option(b'inject_lists', 1)
-        L.fb_set_option(b'interleaved_inject', 1)
+        L.fb_set_option(b'sweepq', 1)
     assert bits_equal(out, seg) and bits_equal(out, planes)
     assert np.array_equal(out64.view(np.uint64), seg64.view(np.uint64))
     for i in (0, 1, 2, 3, F - 1):
@@ -872,9 +891,9 @@ def test_injection_lists_vs_segments(fb, orc):
         assert bits_equal(out[i], ref), i
 
 
-def test_3d_volume_hybrid_kernels(fb, orc):
-    """ a volume with >= 1184 line groups in every sweep: all three hybrid kernel modes (transposing x sweep,
-    in-place y sweep, finalising z sweep) against the oracle, bit for bit """
+def test_3d_volume_kernels(fb, orc):
+    """ a volume with >= 1184 line groups in every sweep: all three kernel modes (transposing x sweep, in-place y sweep,
+    finalising z sweep) against the oracle, bit for bit """
     rng = np.random.default_rng(31)
     size = (160, 128, 160)
     step = 0.25
@@ -948,14 +967,13 @@ def test_sweepq_wide_kernels_vs_oracle(fb, orc, T):
     assert bits_equal(a, ref)
 
 
-def test_spare_buffers_after_interleaved_x_sweep(fb, orc):
-    """ An x sweep that reads interleaved (value, weight) nodes followed by sweeps that are NOT in place -- a kernel so
-    wide that a launch takes one pass (2D), a 3D y sweep split into several launches: the later launches must write
-    planes into the free buffer pair, not into the interleaved alias the x sweep read (advisor finding, round 1). """
+def test_spare_buffers_with_very_wide_kernels(fb, orc):
+    """ Kernels so wide that their rings do not fit on chip: the grid takes the first-generation path, where a launch
+    covers one pass (2D) or the y sweep of a volume is split into several launches that are NOT in place -- the later
+    launches must write into the free buffer pair (advisor finding, round 1). """
     torch = pytest.importorskip('torch')
     rng = np.random.default_rng(222)
-    # 2D: T_y = 449 -> one pass per launch on y (ping-pong between the buffer pairs); 24 fields x 57 line groups feed the
-    # tensor-memory x sweep that reads interleaved nodes
+    # 2D: T_y = 449 -> one pass per launch on y (ping-pong between the buffer pairs)
     size, nf, N = (48, 912), 24, 600
     step = 1.0
     sig = [8.0, 520.0]
@@ -967,7 +985,7 @@ def test_spare_buffers_after_interleaved_x_sweep(fb, orc):
         ref = orc.barnes(pts[i], val[i], sig, [0.0, 0.0], step, size, num_iter=4, nthreads=8)
         assert bits_equal(out[i], ref), i
     # 3D: T_y = 222 with three passes -> the y sweep runs as 2 + 1 passes, the second launch is not in place
-    size3 = (40, 460, 44)                              # 44 planes x 29 line groups >= 1184 work items: interleaved x sweep
+    size3 = (40, 460, 44)
     sig3 = [6.0, 223.0, 5.0]
     n3 = 3
     assert fb.get_half_kernel_size_opt(sig3[1], 1.0, n3) >= 222

@@ -12,7 +12,7 @@ __global__ void k(double *out, int iters, double a, double b, float fa, float fb
 #pragma unroll
     for (int i = 0; i < ND; ++i) x[i] = a + i + threadIdx.x;
 #pragma unroll
-    for (int i = 0; i < NI; ++i) { f[i] = fa + i; n[i] = ia + i; }
+    for (int i = 0; i < NI; ++i) { f[i] = fa + i + threadIdx.x; n[i] = ia + i + threadIdx.x; }
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
@@ -21,7 +21,8 @@ __global__ void k(double *out, int iters, double a, double b, float fa, float fb
                 if (i < ND) x[i] = __dadd_rn(x[i], b);
                 if (i < NI) {
                     if (KIND == 0) f[i] = __fmaf_rn(f[i], fb, fa);
-                    else n[i] = n[i] * ia + 7;
+                    else if (KIND == 1) n[i] = n[i] * ia + 7;
+                    else n[i] = (n[i] ^ ia) + i;          // ALU pipe: one LOP3 / IADD3 pair
                 }
             }
         }
@@ -55,7 +56,7 @@ void run(int warps_per_sm)
     const double cycles = ms * 1e-3 * clk * 1e3;
     const double per_smsp_iter = cycles / iters / 4 / (warps_per_sm / 4);   // cycles per (warp, r-iteration) on one scheduler
     printf("fp64 %d + %s %d per iteration, %d warps/scheduler: %.2f cycles per warp-iteration (fp64 alone would be %d, other alone %d)\n",
-           ND, KIND == 0 ? "FFMA" : "IMAD", NI, warps_per_sm / 4, per_smsp_iter, 2 * ND, NI);
+           ND, KIND == 0 ? "FFMA" : (KIND == 1 ? "IMAD" : "LOP3+IADD3 pairs"), NI, warps_per_sm / 4, per_smsp_iter, 2 * ND, NI);
     cudaFree(d);
 }
 
@@ -71,6 +72,10 @@ int main()
         run<8, 8, 1>(w);
         run<8, 16, 1>(w);
         run<0, 16, 1>(w);
+        run<8, 4, 2>(w);
+        run<8, 8, 2>(w);
+        run<0, 8, 2>(w);
+        run<8, 4, 1>(w);
     }
     return 0;
 }

@@ -9,7 +9,7 @@ if [ "$1" != "nocheck" ]; then
   timeout 300 python tools/q_lab.py check > gpurun_out/check.log 2>&1; echo "check rc=$?"; grep -v "^\[fb\]" gpurun_out/check.log | grep -v '"q_equals_gen1": true' | tail -15
 fi
 echo "== default build"; timeout 300 python tools/q_lab.py time 2>&1 | grep -v "^\[fb\]" | tee gpurun_out/time_default.log
-DEF='[{"sweepq":1,"sweepq_finalize_warps":1},{"sweepq":1,"sweepq_finalize_warps":0}]'
+DEF='[{"sweepq":1}]'
 VS="${QLAB_VARIANT_SETTINGS:-$DEF}"
 for v in fast-barnes-py_b200/csrc/_build/v_*/libfastbarnes_b200.so; do
   [ -f "$v" ] || continue
