@@ -11,6 +11,7 @@
 #include "fb_sweep32.cuh"
 #include "fb_sweepq.cuh"
 #include "fb_line1d.cuh"
+#include "fb_sweepp.cuh"
 
 #include <atomic>
 #include <cmath>
@@ -35,6 +36,7 @@ std::atomic<int> g_inject_lists{1};
 std::atomic<int> g_sweepq{1};
 std::atomic<int> g_q_nst{3};        // staging slots (chunks of rows in flight) per warp
 std::atomic<int> g_q_pf{0};         // extra chunks of lead of the L2 prefetch (0: none)
+std::atomic<int> g_sweepp{1};       // small batches: pass-parallel sweeps (fb_sweepp.cuh): 0 off, 1 when the batch is small, 2 always
 std::atomic<int> g_line1d{1};       // 1D grids: the two-warp line kernel (fb_line1d.cuh) for the exact walk
 std::atomic<int> g_q_warps{8};      // warps per CTA the plan starts with (8 or 4)
 // q path: injection as sort by cell + segmented reduce feeding the x sweep (fb_sparse.cuh) instead of dense grids
@@ -887,22 +889,55 @@ int run_inject(const fb_problem *pr, const Derived &d, long long nsamples, const
 // hybrid kernel in a single launch (2D / 3D whole-grid path only; the z-slab path keeps planes).
 // The q path (fb_sweepq.cuh) runs every axis of a 2D / 3D fp64 grid on interleaved nodes; it needs a kernel
 // of at least 8 elements (D = 2T+2 >= 8) and on-chip rings on every axis.
+// Per axis the grids of interleaved nodes are swept by the q kernels (fb_sweepq.cuh: every axis needs a kernel of at least 8
+// elements, D = 2T+2 >= 8, and on-chip rings) or, when the axis offers the q kernels too few units of work to fill the GPU,
+// by the pass-parallel kernels (fb_sweepp.cuh: any kernel whose rings fit in shared memory).
+struct SweepPPlan { bool ok; int DL, RL, NL; size_t smem; };
+SweepPPlan sweepp_plan(int npass, int T);
+enum { FB_AXIS_NONE = 0, FB_AXIS_Q = 1, FB_AXIS_P = 2 };
+inline int axis_mode(const fb_problem *pr, int m) { return m == 0 ? 1 : (m == pr->dim - 1 ? 2 : 0); }
+// units of work (16-line groups) the q kernel of axis m has
+inline long long axis_q_items(const fb_problem *pr, const Derived &d, int m)
+{
+    const long long nf = pr->nfields;
+    if (m == 0) return nf * d.Dz * ((d.H + 15) / 16);
+    if (m == 1) return pr->dim == 2 ? nf * ((d.W + 15) / 16) : nf * d.Dz * ((d.W + 15) / 16);
+    return nf * ((d.H * d.W + 15) / 16);
+}
+int axis_path(const fb_problem *pr, const Derived &d, int m)
+{
+    const bool q_ok = g_sweepq.load() != 0 && sweepq_plan(pr->num_iter, axis_mode(pr, m), 2 * d.ax[m].T + 2).ok;
+    const int pm = g_sweepp.load();
+    const bool p_ok = pm != 0 && sweepp_plan(pr->num_iter, d.ax[m].T).ok;
+    if (p_ok && (pm >= 2 || !q_ok)) return FB_AXIS_P;
+    // measured on the bench grid (2400 x 1200, T = 27, n = 4): the pass-parallel kernel wins up to 150 q units, ties at 225
+    if (p_ok && 2 * axis_q_items(pr, d, m) <= 3LL * sm_count_current()) return FB_AXIS_P;
+    return q_ok ? FB_AXIS_Q : FB_AXIS_NONE;
+}
+// the grid runs on interleaved nodes when every axis has a kernel for them
+bool use_nodes(const fb_problem *pr, const Derived &d)
+{
+    if (pr->dim < 2 || (pr->flags & FB_FLAG_FP32)) return false;
+    // tensor-map coordinates and the kernels' row offsets are 32-bit
+    if (d.W * d.H > (1LL << 28) || (long long)pr->nfields * d.Dz > (1LL << 30)) return false;
+    for (int m = 0; m < pr->dim; ++m)
+        if (axis_path(pr, d, m) == FB_AXIS_NONE) return false;
+    return true;
+}
+// ... and on the q kernels alone (the z-slab calls, the binned injection)
 bool use_sweepq(const fb_problem *pr, const Derived &d)
 {
     if (pr->dim < 2 || (pr->flags & FB_FLAG_FP32) || g_sweepq.load() == 0) return false;
-    // tensor-map coordinates and the kernels' row offsets are 32-bit
     if (d.W * d.H > (1LL << 28) || (long long)pr->nfields * d.Dz > (1LL << 30)) return false;
-    for (int m = 0; m < pr->dim; ++m) {
-        const int mode = m == 0 ? 1 : (m == pr->dim - 1 ? 2 : 0);
-        if (!sweepq_plan(pr->num_iter, mode, 2 * d.ax[m].T + 2).ok) return false;
-    }
+    for (int m = 0; m < pr->dim; ++m)
+        if (!sweepq_plan(pr->num_iter, axis_mode(pr, m), 2 * d.ax[m].T + 2).ok) return false;
     return true;
 }
 
 // The q path can take its x-sweep input from the binned samples instead of a dense injected grid.
 bool use_sparse(const fb_problem *pr, const Derived &d, long long nsamples, long long max_n)
 {
-    if (g_sparse.load() == 0 || !use_sweepq(pr, d)) return false;
+    if (g_sparse.load() == 0 || !use_sweepq(pr, d) || axis_path(pr, d, 0) != FB_AXIS_Q) return false;
     if (max_n >= FB_BIN_MAX_SAMPLES || (nsamples << pr->dim) >= 0xfffffff0LL) return false;      // record key / index bits
     const FbBins bn = bins_geometry(pr->num_iter, d.ax[0].T, d.W, d.H, (long long)pr->nfields * d.Dz);
     if (!sweepq_plan(pr->num_iter, 1, 2 * d.ax[0].T + 2, 256, sweepqs_prod_bytes(bn.NB), 2).ok) return false;
@@ -970,7 +1005,7 @@ int run_inject_sparse(const fb_problem *pr, const Derived &d, long long nsamples
 }
 
 // the injection writes interleaved (value, weight) nodes exactly when the q path consumes them
-bool inject_interleaved(const fb_problem *pr, const Derived &d) { return use_sweepq(pr, d); }
+bool inject_interleaved(const fb_problem *pr, const Derived &d) { return use_nodes(pr, d); }
 
 // ---- 1D grids: the bit-exact walk of a long line (fb_line1d_kernel) ------------------------------------------------
 struct Line1DPlan { bool ok; int DL, RL; size_t smem; };
@@ -1015,6 +1050,76 @@ int launch_line1d(int npass, const FbLine1D &p, const Line1DPlan &q, long long n
     case 6: return launch_line1d_t<6>(p, q, nfields, st);
     }
     return fail(FB_EINVAL, "unsupported number of fused passes: %d", npass);
+}
+
+// ---- small batches: pass-parallel sweeps (fb_sweepp_kernel) -----------------------------------------------------------
+SweepPPlan sweepp_plan(int npass, int T)
+{
+    SweepPPlan q{false, 0, 0, 0, 0};
+    if (npass < 1 || npass > FB_MAX_FUSED_PASSES) return q;
+    const int T1 = T + 1, D = 2 * T + 2;
+    q.DL = (T1 + FBP_U - 1) / FBP_U + 1;
+    // a stream must hold what lies between its newest write and the oldest element still to be read:
+    // the rows themselves U (PD + 1) + D, the output of a pass U (DL + 1) + T + 1
+    int need = FBP_U * (FBP_PD + 1) + D;
+    if (FBP_U * (q.DL + 1) + T1 > need) need = FBP_U * (q.DL + 1) + T1;
+    q.RL = (need + FBP_U - 1) / FBP_U * FBP_U;
+    const int lpl = npass <= 1 ? 2 : (npass <= 2 ? 4 : (npass <= 4 ? 8 : 16));
+    q.NL = 32 / lpl;
+    q.smem = (size_t)q.NL * (npass + 1) * 2 * (q.RL + 2) * sizeof(double);
+    q.ok = q.smem <= kSmemLimit;
+    return q;
+}
+
+template <int NPASS, int MODE>
+int launch_sweepp_t(const FbSweepP &p, const SweepPPlan &q, cudaStream_t st)
+{
+    static thread_local bool configured[16] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!configured[dev & 15]) {
+        CUDA_TRY(cudaFuncSetAttribute(fb_sweepp_kernel<NPASS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+        CUDA_TRY(cudaFuncSetAttribute(fb_sweepp_kernel<NPASS, MODE>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                      cudaSharedmemCarveoutMaxShared));
+        configured[dev & 15] = true;
+    }
+    const long long items = p.n_outer * p.n_groups;
+    if (items <= 0) return FB_OK;
+    if (items > 2147483647LL) return fail(FB_EINVAL, "too many line groups for the small-batch sweep: %lld", items);
+    fb_sweepp_kernel<NPASS, MODE><<<(unsigned)items, 64, q.smem, st>>>(p);
+    LAUNCH_CHECK();
+    return FB_OK;
+}
+
+template <int MODE>
+int launch_sweepp_m(int npass, const FbSweepP &p, const SweepPPlan &q, cudaStream_t st)
+{
+    switch (npass) {
+    case 1: return launch_sweepp_t<1, MODE>(p, q, st);
+    case 2: return launch_sweepp_t<2, MODE>(p, q, st);
+    case 3: return launch_sweepp_t<3, MODE>(p, q, st);
+    case 4: return launch_sweepp_t<4, MODE>(p, q, st);
+    case 5: return launch_sweepp_t<5, MODE>(p, q, st);
+    case 6: return launch_sweepp_t<6, MODE>(p, q, st);
+    }
+    return fail(FB_EINVAL, "unsupported number of fused passes: %d", npass);
+}
+
+// one axis: src / dst are grids of interleaved (value, weight) nodes
+int run_sweepp(int mode, int num_iter, const AxisParams &ax, const double *src, double *dst, float *out32, double *out64,
+               const unsigned long long *mm, double csf, long long n_outer, long long L, long long n_inner, cudaStream_t st)
+{
+    const SweepPPlan q = sweepp_plan(num_iter, ax.T);
+    if (!q.ok) return fail(FB_EKERNEL, "internal: the small-batch sweep does not cover T=%d, num_iter=%d", ax.T, num_iter);
+    if (L > 2147483647LL - 64LL * (ax.T + 2) * (num_iter + 1)) return fail(FB_EINVAL, "line too long: %lld", L);
+    FbSweepP p{};
+    p.in = src; p.out = dst; p.out32 = out32; p.out64 = out64; p.mm = mm;
+    p.n_outer = n_outer; p.L = L; p.n_inner = n_inner; p.n_groups = (n_inner + q.NL - 1) / q.NL;
+    p.T = ax.T; p.D = 2 * ax.T + 2; p.DL = q.DL; p.RL = q.RL;
+    p.alpha = ax.alpha; p.csf = csf;
+    if (mode == 0) return launch_sweepp_m<0>(num_iter, p, q, st);
+    if (mode == 1) return launch_sweepp_m<1>(num_iter, p, q, st);
+    return launch_sweepp_m<2>(num_iter, p, q, st);
 }
 
 int run_sweeps(const fb_problem *pr, const Derived &d, Workspace &w, float *d_out, double *d_out64, cudaStream_t st,
@@ -1076,9 +1181,11 @@ int run_sweeps(const fb_problem *pr, const Derived &d, Workspace &w, float *d_ou
         if (rc != FB_OK) return rc;
         return prof_mark(5, st);
     }
-    if (use_sweepq(pr, d)) {
-        // interleaved nodes throughout: A (injected, [..][x][y]) -> B (natural order) -> float32 field
+    if (use_nodes(pr, d)) {
+        // interleaved nodes throughout: A (injected, [..][x][y]) -> B (natural order) -> float32 field; per axis the q kernel
+        // or, for small batches, the pass-parallel kernel
         double *a2 = w.vA, *b2 = w.vB;                   // vB and wB are adjacent: one block of 2 g bytes
+        const bool px = axis_path(pr, d, 0) == FB_AXIS_P, py = axis_path(pr, d, 1) == FB_AXIS_P;
         if (sparse) {
             // the x sweep synthesises its rows from the binned samples (run_inject_sparse)
             const int D = 2 * d.ax[0].T + 2;
@@ -1097,22 +1204,30 @@ int run_sweeps(const fb_problem *pr, const Derived &d, Workspace &w, float *d_ou
             p.bin_start = w.bin_start;
             p.nodes = w.bin_rec;
             rc = launch_sweepqs(n, p, q, st);
+        } else if (px) {
+            rc = run_sweepp(1, n, d.ax[0], a2, b2, nullptr, nullptr, w.mm, d.csf, nf * d.Dz, d.W, d.H, st);
         } else {
             rc = run_sweepq(1, n, d.ax[0], a2, b2, nullptr, nullptr, w.mm, d.csf, nf * d.Dz, d.W, d.H, st, ctr);
         }
         if (rc != FB_OK) return rc;
         if ((rc = prof_mark(3, st)) != FB_OK) return rc;
         if (pr->dim == 2) {
-            rc = run_sweepq(2, n, d.ax[1], b2, nullptr, d_out, d_out64, w.mm, d.csf, nf, d.H, d.W, st, ctr);
+            if (py) rc = run_sweepp(2, n, d.ax[1], b2, nullptr, d_out, d_out64, w.mm, d.csf, nf, d.H, d.W, st);
+            else rc = run_sweepq(2, n, d.ax[1], b2, nullptr, d_out, d_out64, w.mm, d.csf, nf, d.H, d.W, st, ctr);
             if (rc != FB_OK) return rc;
             return prof_mark(4, st);
         }
-        // y sweep in place (pass 1 re-reads a row before the last pass overwrites it: needs >= 2 passes)
-        double *c2 = n >= 2 ? b2 : a2;
-        rc = run_sweepq(0, n, d.ax[1], b2, c2, nullptr, nullptr, w.mm, d.csf, nf * d.Dz, d.H, d.W, st, ctr);
+        // y sweep in place (the q kernel's pass 1 re-reads a row before the last pass overwrites it: it needs >= 2 passes;
+        // the pass-parallel kernel reads every row once, ahead of its writes)
+        double *c2 = (py || n >= 2) ? b2 : a2;
+        if (py) rc = run_sweepp(0, n, d.ax[1], b2, c2, nullptr, nullptr, w.mm, d.csf, nf * d.Dz, d.H, d.W, st);
+        else rc = run_sweepq(0, n, d.ax[1], b2, c2, nullptr, nullptr, w.mm, d.csf, nf * d.Dz, d.H, d.W, st, ctr);
         if (rc != FB_OK) return rc;
         if ((rc = prof_mark(4, st)) != FB_OK) return rc;
-        rc = run_sweepq(2, n, d.ax[2], c2, nullptr, d_out, d_out64, w.mm, d.csf, nf, d.Dz, d.H * d.W, st, ctr);
+        if (axis_path(pr, d, 2) == FB_AXIS_P)
+            rc = run_sweepp(2, n, d.ax[2], c2, nullptr, d_out, d_out64, w.mm, d.csf, nf, d.Dz, d.H * d.W, st);
+        else
+            rc = run_sweepq(2, n, d.ax[2], c2, nullptr, d_out, d_out64, w.mm, d.csf, nf, d.Dz, d.H * d.W, st, ctr);
         if (rc != FB_OK) return rc;
         return prof_mark(5, st);
     }
@@ -2185,6 +2300,7 @@ FB_EXPORT int fb_set_option(const char *name, int value)
     if (!strcmp(name, "sweepq_prefetch")) { g_q_pf.store(value); return FB_OK; }
     if (!strcmp(name, "sweepq_warps")) { g_q_warps.store(value); return FB_OK; }
     if (!strcmp(name, "sparse_inject")) { g_sparse.store(value); return FB_OK; }
+    if (!strcmp(name, "sweepp")) { g_sweepp.store(value); return FB_OK; }
     if (!strcmp(name, "line1d")) { g_line1d.store(value); return FB_OK; }
     return fail(FB_EINVAL, "unknown option: %s", name);
 }

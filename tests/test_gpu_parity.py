@@ -268,11 +268,11 @@ def test_chunked_host_pipeline_and_kernel_variants(fb):
         b = fb.barnes_batched(p3, v3, 1.2, [0.0, 0.0], 0.1, size, num_iter=5)
         _lib.check(L.fb_set_option(b'host_chunk_fields', 4))
         b_ref = fb.barnes_batched(p3, v3, 1.2, [0.0, 0.0], 0.1, size, num_iter=5)
-        _lib.check(L.fb_set_option(b'sweepq', 0))
+        _lib.check(L.fb_set_option(b'sweepq', 0)); _lib.check(L.fb_set_option(b'sweepp', 0))
         c = fb.barnes_batched(pts, val, 1.2, [0.0, 0.0], 0.1, size, sample_offsets=offs, num_iter=4)
     finally:
         L.fb_set_option(b'host_chunk_fields', 4)
-        L.fb_set_option(b'sweepq', 1)
+        L.fb_set_option(b'sweepq', 1); L.fb_set_option(b'sweepp', 1)
     assert bits_equal(a, ref) and bits_equal(c, ref) and bits_equal(b, b_ref)
     for i in range(len(counts)):
         single = fb.barnes(pts[offs[i]:offs[i + 1]], val[offs[i]:offs[i + 1]], 1.2, [0.0, 0.0], 0.1, size, num_iter=4)
@@ -803,10 +803,10 @@ def test_large_batch_kernels(fb, orc, ratio, iters):
         for method in (('optimized_convolution', 'convolution') if n == 4 else ('optimized_convolution',)):
             out, _ = run(method, n)
             try:
-                _lib.check(L.fb_set_option(b'sweepq', 0))
+                _lib.check(L.fb_set_option(b'sweepq', 0)); _lib.check(L.fb_set_option(b'sweepp', 0))
                 smem, _ = run(method, n)
             finally:
-                L.fb_set_option(b'sweepq', 1)
+                L.fb_set_option(b'sweepq', 1); L.fb_set_option(b'sweepp', 1)
             assert bits_equal(out, smem), (n, method)
             for i in (0, 17, F - 1):
                 ref = orc.barnes(pts[i], val[i], 1.0, [0.0, 0.0], step, size, method=method, num_iter=n, nthreads=4)
@@ -864,11 +864,11 @@ def test_injection_lists_vs_segments(fb, orc):
         _lib.check(L.fb_set_option(b'inject_lists', 0))
         seg = plan(d_pts, d_val).cpu().numpy()
         seg64 = plan.out64.cpu().numpy()
-        _lib.check(L.fb_set_option(b'sweepq', 0))         # planes of values / weights, first-generation sweeps
+        _lib.check(L.fb_set_option(b'sweepq', 0)); _lib.check(L.fb_set_option(b'sweepp', 0))         # planes of values / weights, first-generation sweeps
         planes = plan(d_pts, d_val).cpu().numpy()
     finally:
         L.fb_set_option(b'inject_lists', 1)
-        L.fb_set_option(b'sweepq', 1)
+        L.fb_set_option(b'sweepq', 1); L.fb_set_option(b'sweepp', 1)
     assert bits_equal(out, seg) and bits_equal(out, planes)
     assert np.array_equal(out64.view(np.uint64), seg64.view(np.uint64))
     for i in (0, 1, 2, 3, F - 1):
@@ -912,9 +912,12 @@ def test_3d_volume_kernels(fb, orc):
 # second-generation sweep kernels (csrc/fb_sweepq.cuh): one warp = 16 lines x all passes, TMA row staging, rings in tensor
 # and shared memory.  They are the default for 2D / 3D fp64 grids whose kernels have 2T+2 >= 8 elements on every axis.
 
-def _q_option(value):
+def _q_option(value, small_batch=0):
+    """ sweepq on / off; the small-batch kernels (fb_sweepp.cuh), which would take over for the few fields of these
+    tests, are off unless asked for (1: when the batch is small -- the default of the library, 2: always) """
     from fastbarnes import _lib
     _lib.check(_lib.lib().fb_set_option(b'sweepq', value))
+    _lib.check(_lib.lib().fb_set_option(b'sweepp', small_batch))
 
 
 @pytest.mark.parametrize('dim,size,ratio,nf,iters', [
@@ -945,9 +948,12 @@ def test_sweepq_vs_first_generation(fb, dim, size, ratio, nf, iters):
             a, a64 = plan(d_pts, d_val).cpu().numpy(), plan.out64.cpu().numpy()
             _q_option(0)
             b, b64 = plan(d_pts, d_val).cpu().numpy(), plan.out64.cpu().numpy()
+            _q_option(1, small_batch=2)
+            c, c64 = plan(d_pts, d_val).cpu().numpy(), plan.out64.cpu().numpy()
         finally:
-            _q_option(1)
+            _q_option(1, small_batch=1)
         assert bits_equal(a, b) and bits_equal(a64, b64), (dim, size, n)
+        assert bits_equal(a, c) and bits_equal(a64, c64), ('small-batch kernels', dim, size, n)
 
 
 @pytest.mark.parametrize('T', [28, 40, 54, 59])
@@ -962,9 +968,14 @@ def test_sweepq_wide_kernels_vs_oracle(fb, orc, T):
     pts = rng.uniform(0, 1, (3000, 2)) * (np.asarray(size) - 1)
     pts[:100] = pts[100:200]
     val = rng.normal(1000, 10, 3000)
-    a = fb.barnes(pts, val, s, [0.0, 0.0], 1.0, size, num_iter=n)
     ref = orc.barnes(pts, val, s, [0.0, 0.0], 1.0, size, num_iter=n, nthreads=8)
-    assert bits_equal(a, ref)
+    try:
+        for small_batch in (0, 2):                          # the q kernels, then the small-batch kernels (the default for one field)
+            _q_option(1, small_batch)
+            a = fb.barnes(pts, val, s, [0.0, 0.0], 1.0, size, num_iter=n)
+            assert bits_equal(a, ref), small_batch
+    finally:
+        _q_option(1, small_batch=1)
 
 
 def test_spare_buffers_with_very_wide_kernels(fb, orc):
