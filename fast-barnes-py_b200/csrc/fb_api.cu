@@ -34,6 +34,7 @@ std::atomic<int> g_profiling{0};
 std::atomic<int> g_inject_lists{1};
 // second-generation sweep kernels (fb_sweepq.cuh): 0 off, non-zero (default) on for 2D / 3D fp64 grids they cover
 std::atomic<int> g_sweepq{1};
+std::atomic<int> g_q_reserve{0};    // SMs the q kernels leave free (z-slab runs: room for the exchange kernels)
 std::atomic<int> g_q_nst{3};        // staging slots (chunks of rows in flight) per warp
 std::atomic<int> g_q_pf{0};         // extra chunks of lead of the L2 prefetch (0: none)
 std::atomic<int> g_sweepp{1};       // small batches: pass-parallel sweeps (fb_sweepp.cuh): 0 off, 1 when the batch is small, 2 always
@@ -282,7 +283,11 @@ int launch_sweepq_t(FbSweepQ p, const SweepQPlan &q, cudaStream_t st)
         if (warps < 1) warps = 1;
     }
     long long grid = (nitems + warps - 1) / warps;
-    if (grid > sms) grid = sms;
+    // one CTA per SM, minus the SMs left free for kernels of other streams (the NCCL kernels of a halo exchange cannot start
+    // next to a CTA that holds all of an SM's shared memory)
+    int avail = sms - g_q_reserve.load();
+    if (avail < 1) avail = 1;
+    if (grid > avail) grid = avail;
     const size_t smem = sweepq_smem_bytes(MODE, warps, q.smem_per_warp);
     // tensor memory: the whole SM's 512 columns when two warps share a lane quarter, else what one warp's rings need
     // (small launches may place several CTAs on one SM)
@@ -2301,6 +2306,7 @@ FB_EXPORT int fb_set_option(const char *name, int value)
     if (!strcmp(name, "sweepq_warps")) { g_q_warps.store(value); return FB_OK; }
     if (!strcmp(name, "sparse_inject")) { g_sparse.store(value); return FB_OK; }
     if (!strcmp(name, "sweepp")) { g_sweepp.store(value); return FB_OK; }
+    if (!strcmp(name, "sweepq_reserve_sms")) { g_q_reserve.store(value < 0 ? 0 : value); return FB_OK; }
     if (!strcmp(name, "line1d")) { g_line1d.store(value); return FB_OK; }
     return fail(FB_EINVAL, "unknown option: %s", name);
 }

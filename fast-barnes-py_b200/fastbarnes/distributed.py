@@ -128,7 +128,7 @@ class BarnesSlab3D:
     """
 
     def __init__(self, sigma, x0, step, size, nsamples, method='optimized_convolution', num_iter=4, max_dist=3.5,
-                 group=None, device=None, want_float64=False, nslabs=None, slab=None):
+                 group=None, device=None, want_float64=False, nslabs=None, slab=None, reserve_sms=0):
         import torch
         import torch.distributed as dist
         from . import _lib
@@ -198,6 +198,12 @@ class BarnesSlab3D:
                           if want_float64 else None)
             self.comm_stream = torch.cuda.Stream(device=self.device) if self.use_dist else None
         self.want64 = bool(want_float64)
+        # SMs the sweeps leave free while a halo exchange is in flight.  The sweep kernels are persistent, one CTA per SM
+        # holding all of its shared memory, so the NCCL kernels of the exchange only start where SMs are left free -- and
+        # they need many: measured on 2 B200 (tools/slab_timeline.py, profiles/r2_slab_timeline.json) the exchange runs
+        # beside the interior sweeps with 48 SMs reserved, not with 16, and the sweeps then lose what the overlap gains.
+        # Default 0: the exchange is enqueued early and effectively runs when the sweeps have drained.
+        self.reserve_sms = int(reserve_sms)
         # planes of mine that other ranks need: [z0, z0 + lo_need) and [z1 - hi_need, z1)
         self.lo_need = min(self.zc, self.halo) if self.rank > 0 else 0
         self.hi_need = min(self.zc, self.halo) if self.rank < self.world - 1 else 0
@@ -248,18 +254,23 @@ class BarnesSlab3D:
         a, b = self.halo_lo, self.halo_lo + self.zc
         return self.vB[a:b], self.wB[a:b]
 
-    def exchange(self):
+    def exchange(self, direction=None):
         """ halo exchange with the ranks whose planes lie in the extended window (torch.distributed point-to-point,
-        one batch: NCCL groups the sends and receives).  Runs on the current stream. """
+        one batch: NCCL groups the sends and receives).  Runs on the current stream.
+        direction: None = everything; 'down' = the planes that travel to lower ranks (my lowest planes out, the lowest
+        planes of the ranks above me in); 'up' = the planes that travel to higher ranks.  Every rank must call the same
+        sequence of directions. """
         if not self.use_dist:
             return
         dist = self.dist
         ops = []
         for q, send, recv in self.transfers():
+            send_dir = 'down' if q < self.rank else 'up'            # my planes travel towards q
+            recv_dir = 'up' if q < self.rank else 'down'            # q's planes travel towards me
             for buf in self.planes:
-                if send:
+                if send and direction in (None, send_dir):
                     ops.append(dist.P2POp(dist.isend, buf[send[0] - self.ext0:send[1] - self.ext0], q, self.group))
-                if recv:
+                if recv and direction in (None, recv_dir):
                     ops.append(dist.P2POp(dist.irecv, buf[recv[0] - self.ext0:recv[1] - self.ext0], q, self.group))
         if ops:
             for req in dist.batch_isend_irecv(ops):
@@ -282,21 +293,42 @@ class BarnesSlab3D:
         torch = self.torch
         with torch.cuda.device(self.device):
             main = torch.cuda.current_stream()
+            comm = self.comm_stream
+            L = self._lib.lib()
             self.inject(pts, val)
-            # boundary planes first, then their transfer on the second stream while the interior is swept
+            # the planes the lower ranks need first; they travel ('down') on the second stream while the rest is swept, then
+            # the planes the higher ranks need ('up') while the interior is swept
             lo, hi = self.lo_need, self.hi_need
             if lo + hi >= self.zc:
-                self.sweeps(0, self.zc)
-                lo, hi = self.zc, 0
+                # thin slab: the two boundary regions overlap -- lower part, send down, upper part, send up
+                lo = min(lo, self.zc)
+                self.sweeps(0, lo)
+                comm.wait_stream(main)
+                with torch.cuda.stream(comm):
+                    self.exchange('down')
+                L.fb_set_option(b'sweepq_reserve_sms', self.reserve_sms)
+                try:
+                    self.sweeps(lo, self.zc - lo)
+                finally:
+                    L.fb_set_option(b'sweepq_reserve_sms', 0)
+                comm.wait_stream(main)
+                with torch.cuda.stream(comm):
+                    self.exchange('up')
             else:
                 self.sweeps(0, lo)
-                self.sweeps(self.zc - hi, hi)
-            self.comm_stream.wait_stream(main)
-            with torch.cuda.stream(self.comm_stream):
-                self.exchange()
-            if lo + hi < self.zc:
-                self.sweeps(lo, self.zc - lo - hi)
-            main.wait_stream(self.comm_stream)
+                comm.wait_stream(main)
+                with torch.cuda.stream(comm):
+                    self.exchange('down')
+                L.fb_set_option(b'sweepq_reserve_sms', self.reserve_sms)
+                try:
+                    self.sweeps(self.zc - hi, hi)
+                    comm.wait_stream(main)
+                    with torch.cuda.stream(comm):
+                        self.exchange('up')
+                    self.sweeps(lo, self.zc - lo - hi)
+                finally:
+                    L.fb_set_option(b'sweepq_reserve_sms', 0)
+            main.wait_stream(comm)
         return self.phase2()
 
 
