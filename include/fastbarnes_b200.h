@@ -229,17 +229,19 @@ int fb_barnes_s2_map_host(int64_t nsamples, const double *pts, const double *val
 
 /* ---- tuning ------------------------------------------------------------------------------- */
 /* process-wide tuning switches that never change results (bit-identical either way):
- *   "two_warp_sweeps" (default 1): sweep launches that fuse >= 2 passes use two warps per 16 lines
- *   "three_warp_sweeps" (default 1): 0 off, 1 three pipeline stages for the finalising sweep, 2 for all
- *   "tmem_sweeps" (default 1): tensor memory as ring storage of the fp64 sweeps: 0 off, non-zero: hybrid
- *       kernel (private rings in TMEM, hand-over ring in shared memory, 16 warps per SM) for launches
- *       with >= 8 work items per SM
- *   "interleaved_inject" (default 1): the fp64 injection writes interleaved (value, weight) nodes whenever the
- *       hybrid kernel runs the x sweep in one launch (one DRAM sector per record instead of two)
+ *   "sweepq" (default 1): 2D / 3D fp64 grids run on interleaved (value, weight) nodes with the q kernels (TMA row
+ *       staging, rings in tensor + shared memory) wherever 2T+2 >= 8 and the rings fit on chip; 0: first-generation kernel
+ *   "sweepq_stages" (default 3), "sweepq_prefetch" (default 0), "sweepq_warps" (default 8): staging slots per warp, extra
+ *       L2 prefetch lead in chunks, warps per CTA of the q kernels
+ *   "sweepq_reserve_sms" (default 0): SMs the persistent q kernels leave free (room for kernels of other streams)
+ *   "sweepp" (default 1): pass-parallel kernels for small batches: 0 off, 1 per axis when the q kernel would have at most
+ *       1.5 x SMs units of work (or cannot run), 2 always
+ *   "line1d" (default 1): 1D grids of >= 1024 points run the two-warp line kernel; 0: lane-pair walk
+ *   "sparse_inject" (default 0): the x sweep synthesises its rows from the samples binned by cell instead of reading a
+ *       dense injection grid (large device-resident batches only; measured slower than the dense path)
  *   "inject_lists" (default 1): with interleaved nodes, link the records of a node into a list (two passes over
  *       the samples) instead of count / allocate / place (three)
- *   "sweep2_na_shift" (default 0): moves passes between the two warps of the two-warp kernel
- *   "host_chunk_fields" (default 4): fields per chunk of the pipelined fb_barnes_host path      */
+ *   "host_chunk_fields" (default 16): fields per chunk of the pipelined fb_barnes_host path     */
 int  fb_set_option(const char *name, int value);
 
 /* ---- introspection for benchmarks --------------------------------------------------------- */
