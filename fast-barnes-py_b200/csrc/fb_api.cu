@@ -1485,14 +1485,20 @@ FB_EXPORT int fb_barnes_host(const fb_problem *prob, int64_t nsamples, const int
     const bool chunked = nf >= 2 * cf;
     if (!chunked) cf = nf;
     const int ns = chunked ? kHostStreams : 1;
-    const long long nchunks = (nf + cf - 1) / cf;
+    // chunk boundaries: the first chunk is a quarter of the others -- nothing overlaps its upload and its kernels, and the
+    // device -> host copies, which bound the call, start that much earlier
+    std::vector<long long> cb;
+    cb.push_back(0);
+    if (chunked && cf >= 4) cb.push_back(cf / 4);
+    while (cb.back() < nf) cb.push_back(cb.back() + cf < nf ? cb.back() + cf : nf);
+    const long long nchunks = (long long)cb.size() - 1;
 
     // per-slot sizes: worst-case chunk
     fb_problem cp = *prob;
     cp.nfields = cf;
     long long max_chunk_samples = 0;
     for (long long c = 0; c < nchunks; ++c) {
-        const long long b0 = c * cf, b1 = (b0 + cf < nf) ? b0 + cf : nf;
+        const long long b0 = cb[c], b1 = cb[c + 1];
         const long long n = sample_offsets ? sample_offsets[b1] - sample_offsets[b0] : (b1 - b0) * max_n;
         if (n > max_chunk_samples) max_chunk_samples = n;
     }
@@ -1512,7 +1518,7 @@ FB_EXPORT int fb_barnes_host(const fb_problem *prob, int64_t nsamples, const int
     for (long long c = 0; c < nchunks; ++c) {
         const int slot = (int)(c % ns);
         cudaStream_t st = chunked ? g_host_streams[slot] : (cudaStream_t)0;
-        const long long b0 = c * cf, b1 = (b0 + cf < nf) ? b0 + cf : nf;
+        const long long b0 = cb[c], b1 = cb[c + 1];
         const long long s0 = sample_offsets ? sample_offsets[b0] : b0 * max_n;
         const long long s1 = sample_offsets ? sample_offsets[b1] : b1 * max_n;
         const long long n = s1 - s0;
@@ -1531,12 +1537,19 @@ FB_EXPORT int fb_barnes_host(const fb_problem *prob, int64_t nsamples, const int
         float *d_out = s.take<float>(cgrid);
         double *d_out64 = out64 ? s.take<double>(cgrid) : nullptr;
         const size_t g = (size_t)(b1 - b0) * d.total;
-        CUDA_TRY(cudaMemcpyAsync(d_pts, pts + (size_t)s0 * prob->dim, (size_t)n * prob->dim * 8, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaMemcpyAsync(d_val, val + s0, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+        // an error leaves the loop, not the function: work of earlier chunks is still in flight on the other streams and
+        // the arena mutex must not be released before they have drained (below)
+        auto copy = [&](void *dst, const void *src, size_t bytes, cudaMemcpyKind kind) {
+            const cudaError_t e = cudaMemcpyAsync(dst, src, bytes, kind, st);
+            if (e != cudaSuccess) rc = fail(FB_ECUDA, "cudaMemcpyAsync failed: %s", cudaGetErrorString(e));
+            return e == cudaSuccess;
+        };
+        if (!copy(d_pts, pts + (size_t)s0 * prob->dim, (size_t)n * prob->dim * 8, cudaMemcpyHostToDevice)) break;
+        if (!copy(d_val, val + s0, (size_t)n * 8, cudaMemcpyHostToDevice)) break;
         rc = pipeline(&cp, n, offs, d_pts, d_val, d_out, d_out64, (char *)ws + (size_t)slot * ws_slot, (long long)ws_slot, st, false);
         if (rc != FB_OK) break;
-        CUDA_TRY(cudaMemcpyAsync(out + (size_t)b0 * d.total, d_out, g * 4, cudaMemcpyDeviceToHost, st));
-        if (out64) CUDA_TRY(cudaMemcpyAsync(out64 + (size_t)b0 * d.total, d_out64, g * 8, cudaMemcpyDeviceToHost, st));
+        if (!copy(out + (size_t)b0 * d.total, d_out, g * 4, cudaMemcpyDeviceToHost)) break;
+        if (out64 && !copy(out64 + (size_t)b0 * d.total, d_out64, g * 8, cudaMemcpyDeviceToHost)) break;
     }
     if (chunked) {
         for (int i = 0; i < ns; ++i) {

@@ -414,6 +414,19 @@ def get_sigma_effective(sigma, step, num_iter):
 # ---------------------------------------------------------------------------------------------
 # device-resident interface (torch supplies device memory and streams; plumbing only)
 
+def _check_sample_offsets(sample_offsets, nfields, nsamples):
+    """ None, or nfields + 1 non-decreasing offsets from 0 to nsamples as a contiguous int64 array (the C side reads exactly
+    nfields + 1 entries). """
+    if sample_offsets is None:
+        return None
+    off = np.ascontiguousarray(sample_offsets, dtype=np.int64).reshape(-1)
+    if len(off) != nfields + 1:
+        raise RuntimeError('sample_offsets must have nfields + 1 = %d entries: %d' % (nfields + 1, len(off)))
+    if off[0] != 0 or off[-1] != nsamples or np.any(np.diff(off) < 0):
+        raise RuntimeError('sample_offsets must be non-decreasing, start at 0 and end at nsamples')
+    return off
+
+
 class BarnesDevice:
     """
     Device-resident plan for repeated interpolation of `nfields` fields with `nsamples_total`
@@ -434,6 +447,8 @@ class BarnesDevice:
             raise RuntimeError('no CUDA device available; this package has no CPU fallback')
         self.torch = torch
         self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.device.index is None:
+            self.device = torch.device('cuda', torch.cuda.current_device())
         self.dim = dim
         sigma = _per_axis('sigma', sigma, dim)
         x0 = _per_axis('x0', x0, dim)
@@ -444,7 +459,7 @@ class BarnesDevice:
         self.nsamples = int(nsamples)
         self.prob = _problem(dim, sigma, x0, step, self.size, _CONV_METHODS[method], num_iter,
                              exp(-max_dist ** 2 / 2), nfields, _precision_flag(precision, dim, want_float64))
-        self.offsets = None if sample_offsets is None else np.ascontiguousarray(sample_offsets, dtype=np.int64)
+        self.offsets = _check_sample_offsets(sample_offsets, self.nfields, self.nsamples)
         L = _lib.lib()
         nbytes = L.fb_workspace_bytes(self.prob, self.nsamples)
         if nbytes < 0:
@@ -465,6 +480,13 @@ class BarnesDevice:
             raise RuntimeError('pts and val must be contiguous')
         if pts.numel() != self.nsamples * self.dim or val.numel() != self.nsamples:
             raise RuntimeError('unexpected number of samples')
+        if pts.device != self.device or val.device != self.device:
+            raise RuntimeError('pts and val must live on the device of the plan (%s)' % (self.device,))
+        if out is not None:
+            shape = (self.nfields,) + tuple(self.size[::-1])
+            if (not out.is_cuda or out.dtype != torch.float32 or not out.is_contiguous() or tuple(out.shape) != shape
+                    or out.device != self.device):
+                raise RuntimeError('out must be a contiguous float32 CUDA tensor of shape %s on %s' % (shape, self.device))
         out = self.out if out is None else out
         L = _lib.lib()
         with torch.cuda.device(self.device):

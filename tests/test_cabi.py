@@ -136,3 +136,15 @@ def test_product_never_imports_the_oracle():
             if f.endswith(('.py', '.cu', '.cuh', '.h')) or f == 'Makefile':
                 txt = open(os.path.join(dirpath, f)).read()
                 assert 'oracle' not in txt.lower() or f == '_none_', os.path.join(dirpath, f)
+
+
+def test_sample_offsets_are_validated_on_the_host():
+    """ BarnesDevice hands sample_offsets to C code that reads exactly nfields + 1 entries: wrong lengths, offsets that do not
+    run from 0 to nsamples or that decrease are refused before anything reaches the device (advisor finding, round 1). """
+    from fastbarnes.interpolation import _check_sample_offsets
+    assert _check_sample_offsets(None, 3, 10) is None
+    ok = _check_sample_offsets([0, 4, 4, 10], 3, 10)
+    assert ok.dtype == np.int64 and ok.flags['C_CONTIGUOUS'] and list(ok) == [0, 4, 4, 10]
+    for bad in ([0, 4, 10], [0, 4, 4, 10, 10], [1, 4, 4, 10], [0, 4, 4, 9], [0, 5, 4, 10]):
+        with pytest.raises(RuntimeError, match='sample_offsets'):
+            _check_sample_offsets(bad, 3, 10)

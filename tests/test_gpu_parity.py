@@ -268,12 +268,19 @@ def test_chunked_host_pipeline_and_kernel_variants(fb):
         b = fb.barnes_batched(p3, v3, 1.2, [0.0, 0.0], 0.1, size, num_iter=5)
         _lib.check(L.fb_set_option(b'host_chunk_fields', 4))
         b_ref = fb.barnes_batched(p3, v3, 1.2, [0.0, 0.0], 0.1, size, num_iter=5)
+        # 13 fields in chunks of 4: a first chunk of one field (a quarter), three full chunks
+        p13 = pts[:offs[1]][None].repeat(13, axis=0) + rng.uniform(0, 0.01, (13, counts[0], 1))
+        v13 = rng.normal(0, 1, (13, counts[0]))
+        q4 = fb.barnes_batched(p13, v13, 1.2, [0.0, 0.0], 0.1, size, num_iter=4)
+        _lib.check(L.fb_set_option(b'host_chunk_fields', 64))
+        q_ref = fb.barnes_batched(p13, v13, 1.2, [0.0, 0.0], 0.1, size, num_iter=4)
+        _lib.check(L.fb_set_option(b'host_chunk_fields', 4))
         _lib.check(L.fb_set_option(b'sweepq', 0)); _lib.check(L.fb_set_option(b'sweepp', 0))
         c = fb.barnes_batched(pts, val, 1.2, [0.0, 0.0], 0.1, size, sample_offsets=offs, num_iter=4)
     finally:
-        L.fb_set_option(b'host_chunk_fields', 4)
+        L.fb_set_option(b'host_chunk_fields', 16)
         L.fb_set_option(b'sweepq', 1); L.fb_set_option(b'sweepp', 1)
-    assert bits_equal(a, ref) and bits_equal(c, ref) and bits_equal(b, b_ref)
+    assert bits_equal(a, ref) and bits_equal(c, ref) and bits_equal(b, b_ref) and bits_equal(q4, q_ref)
     for i in range(len(counts)):
         single = fb.barnes(pts[offs[i]:offs[i + 1]], val[offs[i]:offs[i + 1]], 1.2, [0.0, 0.0], 0.1, size, num_iter=4)
         assert bits_equal(ref[i], single), i
