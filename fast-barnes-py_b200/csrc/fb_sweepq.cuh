@@ -329,29 +329,22 @@ __device__ __forceinline__ void fbq_chunk(const double (&bn)[FBQ_U], const doubl
 // pair trade one operand per row pair: the even lane divides rows kb, kb+2, .., the odd lane rows kb+1, kb+3, ..
 // o32 / o64 point at this lane's first row, its m-th row lies 2 * m * row_elems elements further; bit m of
 // `rows` = that row exists (and the lane's line lies inside the grid).
-// The exchange is split off (fbq_finalize_gather) and runs right after the rows have left the last pass; what the loop
-// carries into the next iteration -- where the divisions overlap with the passes of the next chunk -- are the operands
-// of the divisions, produced by the selects of the exchange, and not a copy of the rows.
-__device__ __forceinline__ void fbq_finalize_gather(const double (&xs)[FBQ_U], int fld, double (&va)[FBQ_U / 2], double (&wa)[FBQ_U / 2])
-{
-#pragma unroll
-    for (int j = 0; j < FBQ_U; j += 2) {
-        const double send = fld ? xs[j] : xs[j + 1];
-        const double recv = __shfl_xor_sync(0xffffffffu, send, 1);
-        va[j / 2] = fld ? recv : xs[j];
-        wa[j / 2] = fld ? xs[j + 1] : recv;
-    }
-}
-
-__device__ __forceinline__ void fbq_finalize_store(const double (&va)[FBQ_U / 2], const double (&wa)[FBQ_U / 2], double csf,
-                                                   double offset, float *o32, double *o64, unsigned row_elems, unsigned rows)
+__device__ __forceinline__ void fbq_finalize_chunk(const double (&xs)[FBQ_U], int fld, double csf, double offset, float *o32,
+                                                   double *o64, unsigned row_elems, unsigned rows)
 {
     constexpr int U = FBQ_U;
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
-    double qa[U / 2];
+    double va[U / 2], wa[U / 2], qa[U / 2];
     bool masked[U / 2];
 #pragma unroll
-    for (int j = 0; j < U / 2; ++j) masked[j] = wa[j] < csf;
+    for (int j = 0; j < U; j += 2) {
+        const double send = fld ? xs[j] : xs[j + 1];
+        const double recv = __shfl_xor_sync(0xffffffffu, send, 1);
+        va[j / 2] = fld ? recv : xs[j];
+        const double ww = fld ? xs[j + 1] : recv;
+        masked[j / 2] = ww < csf;
+        wa[j / 2] = ww;
+    }
     fb_div_n<U / 2>(va, wa, qa, masked);
     double q[U / 2];
 #pragma unroll
@@ -481,9 +474,6 @@ fb_sweepq_kernel(const FbSweepQ p, const __grid_constant__ CUtensorMap tm_in, co
 
         // output of the 8 rows kb .. kb+7 that left the last pass one chunk ago (kb is a multiple of 8, 0 <= kb < L;
         // all_rows: kb + 7 < L)
-        double fva[U / 2], fwa[U / 2];                   // MODE 2: operands of the previous chunk's divisions
-#pragma unroll
-        for (int j = 0; j < U / 2; ++j) { fva[j] = 0.0; fwa[j] = 0.0; }
         auto emit = [&](const double (&x)[U], int kb, bool all_rows) {
             if (MODE == 0 || MODE == 1) {
                 fbq_bulk_wait_read0();                               // the previous tile has been read (whichever lane stored it)
@@ -507,7 +497,7 @@ fb_sweepq_kernel(const FbSweepQ p, const __grid_constant__ CUtensorMap tm_in, co
                     }
                 }
                 const long long o = ((long long)outer * p.L + kb + fld) * p.n_inner + inner;
-                fbq_finalize_store(fva, fwa, p.csf, offset, p.out32 + o, p.out64 ? p.out64 + o : nullptr, (unsigned)p.n_inner, rows);
+                fbq_finalize_chunk(x, fld, p.csf, offset, p.out32 + o, p.out64 ? p.out64 + o : nullptr, (unsigned)p.n_inner, rows);
             }
         };
 
@@ -549,12 +539,8 @@ fb_sweepq_kernel(const FbSweepQ p, const __grid_constant__ CUtensorMap tm_in, co
             __syncwarp();
             issue(t + nst * U, slot, c + nst < nchunks);
             if constexpr (NT > 0) fb_tmem_wait_st();
-            if (MODE == 2) {
-                fbq_finalize_gather(xs, fld, fva, fwa);
-            } else {
 #pragma unroll
-                for (int j = 0; j < U; ++j) xsp[j] = xs[j];
-            }
+            for (int j = 0; j < U; ++j) xsp[j] = xs[j];
             wslot += U; wslot = (wslot >= R) ? 0 : wslot;
             rslot += U; rslot = (rslot >= R) ? rslot - R : rslot;
             ++slot; slot = (slot == nst) ? 0 : slot;
