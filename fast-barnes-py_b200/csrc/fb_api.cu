@@ -40,6 +40,8 @@ std::atomic<int> g_q_pf{0};         // extra chunks of lead of the L2 prefetch (
 std::atomic<int> g_sweepp{1};       // small batches: pass-parallel sweeps (fb_sweepp.cuh): 0 off, 1 when the batch is small, 2 always
 std::atomic<int> g_line1d{1};       // 1D grids: the two-warp line kernel (fb_line1d.cuh) for the exact walk
 std::atomic<int> g_q_warps{8};      // warps per CTA the plan starts with (8 or 4)
+std::atomic<int> g_q_cap_xy{8};     // most warps per CTA of the transposing / in-place sweeps (shared memory and registers an
+std::atomic<int> g_q_cap_fin{8};    // ... of the finalising sweep            SM keeps free for kernels of other streams)
 // q path: injection as sort by cell + segmented reduce feeding the x sweep (fb_sparse.cuh) instead of dense grids
 std::atomic<int> g_sparse{0};       // opt-in: measured slower than the dense path (x sweep 1.55 vs 1.15 ms on the bench batch), see DESIGN.md
 
@@ -278,6 +280,8 @@ int launch_sweepq_t(FbSweepQ p, const SweepQPlan &q, cudaStream_t st)
     const int sms = sm_count(dev);
     // few items: spread them over the SMs with fewer warps per CTA
     int warps = q.warps;
+    const int cap = MODE == 2 ? g_q_cap_fin.load() : g_q_cap_xy.load();
+    if (cap >= 1 && warps > cap) warps = cap;
     if (nitems < (long long)sms * warps) {
         warps = (int)((nitems + sms - 1) / sms);
         if (warps < 1) warps = 1;
@@ -2317,6 +2321,8 @@ FB_EXPORT int fb_set_option(const char *name, int value)
     if (!strcmp(name, "sweepq_stages")) { g_q_nst.store(value); return FB_OK; }
     if (!strcmp(name, "sweepq_prefetch")) { g_q_pf.store(value); return FB_OK; }
     if (!strcmp(name, "sweepq_warps")) { g_q_warps.store(value); return FB_OK; }
+    if (!strcmp(name, "sweepq_cap_warps_xy")) { g_q_cap_xy.store(value); return FB_OK; }
+    if (!strcmp(name, "sweepq_cap_warps_final")) { g_q_cap_fin.store(value); return FB_OK; }
     if (!strcmp(name, "sparse_inject")) { g_sparse.store(value); return FB_OK; }
     if (!strcmp(name, "sweepp")) { g_sweepp.store(value); return FB_OK; }
     if (!strcmp(name, "sweepq_reserve_sms")) { g_q_reserve.store(value < 0 ? 0 : value); return FB_OK; }

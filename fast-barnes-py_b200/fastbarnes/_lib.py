@@ -183,6 +183,11 @@ def lib():
                          ('FB_SWEEPQ_PREFETCH', b'sweepq_prefetch'), ('FB_SWEEPQ_WARPS', b'sweepq_warps')):
             if os.environ.get(env) is not None:
                 L.fb_set_option(opt, int(os.environ[env]))
+        # any option: FB_OPTIONS="name=value,name=value"
+        for item in os.environ.get('FB_OPTIONS', '').split(','):
+            if '=' in item:
+                k, v = item.split('=', 1)
+                check(L.fb_set_option(k.strip().encode(), int(v)))
         _lib = L
     return _lib
 
