@@ -798,8 +798,11 @@ int check_offsets(const fb_problem *pr, long long nsamples, const int64_t *off, 
 // z_off / z_cnt: z window of the injected buffers (z-slab runs); the whole grid is (0, d.Dz).
 int run_inject(const fb_problem *pr, const Derived &d, long long nsamples, const int64_t *h_offsets,
                const double *d_pts, const double *d_val, Workspace &w, cudaStream_t st,
-               long long z_off = 0, long long z_cnt = -1, bool f32 = false, bool il64 = false)
+               long long z_off = 0, long long z_cnt = -1, bool f32 = false, bool il64 = false,
+               const FbSamples *inject_from = nullptr)
 {
+    // inject_from: the samples the injection kernels read (z-slab runs: the compacted list; offsets on the device, at most
+    // nsamples of them); min / max always run over d_pts / d_val
     // il64: the injected grid is ONE array of interleaved double2 (value, weight) nodes in w.vA (FORM 2)
     // f32: the injected grid is ONE array of interleaved float2 (value, weight) nodes in w.vA (fp32 path)
     if (z_cnt < 0) z_cnt = d.Dz;
@@ -841,6 +844,7 @@ int run_inject(const fb_problem *pr, const Derived &d, long long nsamples, const
     if (mmb > 1024) mmb = 1024;
     fb_minmax_kernel<<<dim3((unsigned)mmb, nf), 256, 0, st>>>(s, w.mm);
     LAUNCH_CHECK();
+    if (inject_from) s = *inject_from;
     const dim3 sg((unsigned)((max_n + 255) / 256), nf);
     const long long R = nsamples << pr->dim;
     long long rblocks = (R + 127) / 128;
@@ -1854,6 +1858,9 @@ struct SlabLayout {
     Workspace inj;                  // injection scratch (record tables, min/max)
     size_t off_vB, off_wB;          // byte offsets of the extended B buffers
     size_t off_out, off_out64;      // ... and of the extended result buffers
+    double *pts_c, *val_c;          // samples that touch the slab, in order
+    unsigned int *cmp_cnt, *cmp_start, *cmp_sums;
+    long long *cmp_offsets;         // {0, number of compacted samples} on the device
     size_t bytes;
 };
 
@@ -1887,6 +1894,14 @@ int slab_carve(SlabLayout &s, char *base, const fb_problem *pr, const Derived &d
     s.inj.seg_base = (unsigned int *)take(R * 4 + 4);
     s.inj.seg_n = (unsigned int *)take(R * 4 + 4);
     s.inj.link_next = (unsigned int *)take(R * 4 + 4);
+    // compaction of the samples to those that touch the slab (fb_sparse.cuh)
+    const size_t nblk = ((size_t)nsamples + 255) / 256;
+    s.pts_c = (double *)take((size_t)nsamples * pr->dim * 8 + 8);
+    s.val_c = (double *)take((size_t)nsamples * 8 + 8);
+    s.cmp_cnt = (unsigned int *)take((nblk + 1) * 4);
+    s.cmp_start = (unsigned int *)take((nblk + 2) * 4);
+    s.cmp_sums = (unsigned int *)take((nblk / (FB_SCAN_BLOCK * FB_SCAN_PER_THREAD) + 4) * 4);
+    s.cmp_offsets = (long long *)take(2 * 8);
     s.bytes = off;
     return FB_OK;
 }
@@ -1955,6 +1970,38 @@ FB_EXPORT int fb_slab_layout(const fb_problem *prob, int64_t nsamples, int64_t z
 
 namespace {
 // injection (do_inject) and / or the x and y sweeps of the own planes [pb, pb + pc) of a slab
+// the samples whose cell touches planes [z_begin, z_begin + z_count), in order (slabs that are the whole volume: nothing to do)
+int slab_compact(const fb_problem *prob, const Derived &d, const SlabLayout &s, long long nsamples, const double *d_pts,
+                 const double *d_val, long long z_begin, long long z_count, cudaStream_t st, FbSamples &out, bool &used)
+{
+    used = false;
+    if (z_count >= d.Dz || nsamples < 1024 || nsamples >= (1LL << 31)) return FB_OK;
+    FbGrid gr{};
+    gr.dim = prob->dim;
+    gr.W = d.W; gr.H = d.H; gr.Dz = d.Dz; gr.total = d.W * d.H * z_count;
+    gr.z_off = z_begin; gr.z_cnt = z_count;
+    for (int m = 0; m < 3; ++m) { gr.x0[m] = prob->x0[m]; gr.step[m] = prob->step[m]; }
+    const long long nblk = (nsamples + 255) / 256;
+    fb_slab_compact_count_kernel<<<(unsigned)nblk, 256, 0, st>>>(d_pts, nsamples, gr, s.cmp_cnt);
+    LAUNCH_CHECK();
+    const int nsb = (int)((nblk + FB_SCAN_BLOCK * FB_SCAN_PER_THREAD - 1) / (FB_SCAN_BLOCK * FB_SCAN_PER_THREAD));
+    fb_scan_local_kernel<<<(unsigned)nsb, FB_SCAN_BLOCK, 0, st>>>(s.cmp_cnt, s.cmp_start, s.cmp_sums, nblk);
+    LAUNCH_CHECK();
+    fb_scan_sums_kernel<<<1, 1024, 0, st>>>(s.cmp_sums, nsb, s.cmp_sums + nsb + 1);
+    LAUNCH_CHECK();
+    fb_scan_add_kernel<<<(unsigned)nsb, FB_SCAN_BLOCK, 0, st>>>(s.cmp_start, s.cmp_sums, s.cmp_sums + nsb + 1, nblk);
+    LAUNCH_CHECK();
+    fb_slab_compact_scatter_kernel<<<(unsigned)nblk, 256, 0, st>>>(d_pts, d_val, nsamples, gr, s.cmp_start, nblk, s.pts_c, s.val_c,
+                                                                  s.cmp_offsets);
+    LAUNCH_CHECK();
+    out.pts = s.pts_c;
+    out.val = s.val_c;
+    out.offsets = s.cmp_offsets;
+    out.n_uniform = 0;
+    used = true;
+    return FB_OK;
+}
+
 int slab_phase1(const fb_problem *prob, int64_t z_begin, int64_t z_count, int64_t halo_lo, int64_t halo_hi, int64_t nsamples,
                 const double *d_pts, const double *d_val, int want_out64, void *d_workspace, int64_t workspace_bytes,
                 void *stream, bool do_inject, long long pb, long long pc)
@@ -1974,6 +2021,10 @@ int slab_phase1(const fb_problem *prob, int64_t z_begin, int64_t z_count, int64_
     const long long plane = d.W * d.H;
     // injection into the own planes, held in the middle of the extended A buffers
     Workspace w = s.inj;
+    FbSamples near{};
+    bool compacted = false;
+    if (do_inject && (rc = slab_compact(prob, d, s, nsamples, d_pts, d_val, z_begin, z_count, st, near, compacted)) != FB_OK) return rc;
+    const FbSamples *from = compacted ? &near : nullptr;
     if (slab_interleaved(prob, d)) {
         // interleaved nodes: A2 / B2 are the 2 g byte blocks; the own planes' nodes are one contiguous run
         double *a2 = s.vA + 2 * halo_lo * plane, *b2 = s.vB + 2 * halo_lo * plane;
@@ -1981,7 +2032,7 @@ int slab_phase1(const fb_problem *prob, int64_t z_begin, int64_t z_count, int64_
         w.wA = a2 + z_count * plane;                  // second half of the own planes' block (run_inject zero-fills both halves)
         w.vB = b2;
         w.wB = b2 + z_count * plane;
-        if (do_inject && (rc = run_inject(prob, d, nsamples, nullptr, d_pts, d_val, w, st, z_begin, z_count, false, true)) != FB_OK)
+        if (do_inject && (rc = run_inject(prob, d, nsamples, nullptr, d_pts, d_val, w, st, z_begin, z_count, false, true, from)) != FB_OK)
             return rc;
         if (pc == 0) return FB_OK;
         SweepCounters qctr{w.counters + 4, 0};
@@ -1996,7 +2047,8 @@ int slab_phase1(const fb_problem *prob, int64_t z_begin, int64_t z_count, int64_
     w.wA = s.wA + halo_lo * plane;
     w.vB = s.vB + halo_lo * plane;
     w.wB = s.wB + halo_lo * plane;
-    if (do_inject && (rc = run_inject(prob, d, nsamples, nullptr, d_pts, d_val, w, st, z_begin, z_count)) != FB_OK) return rc;
+    if (do_inject && (rc = run_inject(prob, d, nsamples, nullptr, d_pts, d_val, w, st, z_begin, z_count, false, false, from)) != FB_OK)
+        return rc;
     if (pc == 0) return FB_OK;
     // x sweep (A -> B, transposing) and y sweep (in place) on the planes [pb, pb + pc)
     Pair cur{w.vA + pb * plane, w.wA + pb * plane}, spare{w.vB + pb * plane, w.wB + pb * plane};

@@ -338,3 +338,50 @@ fb_bin_reduce_kernel(FbBins bn, const unsigned int *start, FbRec *rec)
         }
     }
 }
+
+// ------------------------------------------------------------------------------------------
+// z-slab runs: every rank holds all samples, but only those whose cell touches the slab's planes leave records there.
+// Injecting from the full list keeps one lane in eight busy (eight slabs); the samples are therefore compacted first --
+// in order, so that the per-node sums keep the reference's sample order (a stable compaction: per-block counts, the
+// exclusive scan above, scatter at block start + rank inside the block).  Min / max still run over ALL samples (the offset
+// is the global one).
+__device__ __forceinline__ bool fb_slab_keep(const FbGrid &g, const double *pts, long long gi)
+{
+    long long xi, yi, zi;
+    double xw, yw, zw;
+    if (!fb_sample_cell(g, pts, gi, xi, yi, zi, xw, yw, zw)) return false;      // outside the grid: no record anywhere
+    return zi + 1 >= g.z_off && zi < g.z_off + g.z_cnt;                          // planes zi, zi + 1 against the window
+}
+
+__global__ void __launch_bounds__(256)
+fb_slab_compact_count_kernel(const double *pts, long long n, FbGrid g, unsigned int *cnt)
+{
+    const long long k = (long long)blockIdx.x * 256 + threadIdx.x;
+    const int keep = (k < n && fb_slab_keep(g, pts, k)) ? 1 : 0;
+    const int c = __syncthreads_count(keep);
+    if (threadIdx.x == 0) cnt[blockIdx.x] = (unsigned int)c;
+}
+
+__global__ void __launch_bounds__(256)
+fb_slab_compact_scatter_kernel(const double *pts, const double *val, long long n, FbGrid g, const unsigned int *start,
+                               long long nblocks, double *pts_c, double *val_c, long long *offsets_c)
+{
+    __shared__ unsigned int warp_base[8];
+    const long long k = (long long)blockIdx.x * 256 + threadIdx.x;
+    const bool keep = k < n && fb_slab_keep(g, pts, k);
+    const unsigned int m = __ballot_sync(0xffffffffu, keep);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) warp_base[wid] = (unsigned int)__popc(m);
+    __syncthreads();
+    unsigned int base = start[blockIdx.x];
+    for (int w = 0; w < wid; ++w) base += warp_base[w];
+    if (keep) {
+        const long long o = (long long)base + __popc(m & ((1u << lane) - 1u));
+        for (int d = 0; d < g.dim; ++d) pts_c[o * g.dim + d] = pts[k * g.dim + d];
+        val_c[o] = val[k];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        offsets_c[0] = 0;
+        offsets_c[1] = (long long)start[nblocks];
+    }
+}
