@@ -314,7 +314,9 @@ def slab3d_block(torch, dist, dev, rank, world, steps=5, warmup=2):
     pts = rng.uniform(0.0, 1.0, (N, 3)) * np.asarray([W - 1, H - 1, D - 1], dtype=np.float64)
     val = rng.normal(0.0, 1.0, N)
     dp, dv = torch.from_numpy(pts).to(dev), torch.from_numpy(val).to(dev)
-    slab = fd.BarnesSlab3D(sigma, [0.0] * 3, 1.0, (W, H, D), N, num_iter=n_iter, want_float64=True, device=dev)
+    slab = fd.BarnesSlab3D(sigma, [0.0] * 3, 1.0, (W, H, D), N, num_iter=n_iter, want_float64=True, device=dev,
+                           exchange=os.environ.get('FB_SLAB_EXCHANGE', 'nccl'))
+    exchange_mode = slab.exchange_mode
 
     def barrier():
         torch.cuda.synchronize()
@@ -376,7 +378,7 @@ def slab3d_block(torch, dist, dev, rank, world, steps=5, warmup=2):
     torch.cuda.empty_cache()
     return {'workload': 'ONE 1024x1024x512 volume, N=1e7 samples, sigma 8 grid steps, num_iter 4, fp64, device-resident samples; '
                         'z-slabs over %d GPU(s), halo %d planes per side' % (world, halo),
-            'scaling': 'strong', 'n_gpus': world, 'ms_per_volume': ms, 'value': W * H * D / (ms * 1e-3), 'unit': UNIT,
+            'scaling': 'strong', 'n_gpus': world, 'halo_transport': exchange_mode, 'ms_per_volume': ms, 'value': W * H * D / (ms * 1e-3), 'unit': UNIT,
             'steps': steps, 'warmup': warmup,
             'ms_single_gpu_undivided': ms_single,
             'ms_steps_serialised_max_over_ranks': {'inject': parts[0], 'sweeps_xy': parts[1], 'halo_exchange': parts[2],

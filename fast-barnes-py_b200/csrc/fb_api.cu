@@ -2138,6 +2138,61 @@ FB_EXPORT int fb_slab_phase2_inplace_dev(const fb_problem *prob, int64_t z_begin
                        workspace_bytes, stream);
 }
 
+// ---- interprocess events (ordering of the peer-mapped halo exchange of the z-slab runs) -------------------------------
+// One process per GPU: a rank records an event behind the sweeps of the planes its neighbours need; the neighbours, which
+// have opened the event's IPC handle, let their copy stream wait for it before they pull those planes.
+FB_EXPORT int fb_ipc_event_create(void **event, void *handle64)
+{
+    int rc = require_device();
+    if (rc != FB_OK) return rc;
+    if (!event || !handle64) return fail(FB_EINVAL, "null pointer");
+    cudaEvent_t ev;
+    CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming | cudaEventInterprocess));
+    cudaIpcEventHandle_t h;
+    cudaError_t e = cudaIpcGetEventHandle(&h, ev);
+    if (e != cudaSuccess) {
+        cudaEventDestroy(ev);
+        return fail(FB_ECUDA, "cudaIpcGetEventHandle failed: %s", cudaGetErrorString(e));
+    }
+    static_assert(sizeof(cudaIpcEventHandle_t) == 64, "IPC event handle size");
+    memcpy(handle64, &h, 64);
+    *event = (void *)ev;
+    return FB_OK;
+}
+
+FB_EXPORT int fb_ipc_event_open(const void *handle64, void **event)
+{
+    int rc = require_device();
+    if (rc != FB_OK) return rc;
+    if (!event || !handle64) return fail(FB_EINVAL, "null pointer");
+    cudaIpcEventHandle_t h;
+    memcpy(&h, handle64, 64);
+    cudaEvent_t ev;
+    CUDA_TRY(cudaIpcOpenEventHandle(&ev, h));
+    *event = (void *)ev;
+    return FB_OK;
+}
+
+FB_EXPORT int fb_event_record(void *event, void *stream)
+{
+    if (!event) return fail(FB_EINVAL, "null event");
+    CUDA_TRY(cudaEventRecord((cudaEvent_t)event, (cudaStream_t)stream));
+    return FB_OK;
+}
+
+FB_EXPORT int fb_stream_wait_event(void *stream, void *event)
+{
+    if (!event) return fail(FB_EINVAL, "null event");
+    CUDA_TRY(cudaStreamWaitEvent((cudaStream_t)stream, (cudaEvent_t)event, 0));
+    return FB_OK;
+}
+
+FB_EXPORT int fb_event_destroy(void *event)
+{
+    if (event) CUDA_TRY(cudaEventDestroy((cudaEvent_t)event));
+    return FB_OK;
+}
+
 // ---- S2 -------------------------------------------------------------------------------------------------
 // util/lambert_conformal.py:50-94 (host libm, like the Numba code)
 FB_EXPORT int fb_lambert_create_proj(double center_lon, double center_lat, double lat1, double lat2, double *proj)

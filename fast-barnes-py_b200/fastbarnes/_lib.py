@@ -77,6 +77,11 @@ SIGNATURES = {
                                                   ctypes.c_int64, ctypes.c_void_p]),
     'fb_slab_result_offsets': (ctypes.c_int, [ctypes.POINTER(FbProblem), ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
                                               ctypes.c_int64, ctypes.c_int, c_i64_p, c_i64_p]),
+    'fb_ipc_event_create': (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p]),
+    'fb_ipc_event_open': (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p)]),
+    'fb_event_record': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    'fb_stream_wait_event': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    'fb_event_destroy': (ctypes.c_int, [ctypes.c_void_p]),
     'fb_accumulate_lines_host': (ctypes.c_int, [c_double_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
                                                 ctypes.c_int64, ctypes.c_int, ctypes.c_double]),
     'fb_convolve_host': (ctypes.c_int, [ctypes.c_int, c_double_p, c_double_p, c_i64_p, c_i32_p, ctypes.c_int,

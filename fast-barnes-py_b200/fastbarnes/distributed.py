@@ -105,6 +105,31 @@ def slab_transfers(nplanes, world, rank, halo):
     return out
 
 
+class _IpcEvent:
+    """ CUDA event shared between the processes of one node (C ABI fb_ipc_event_*; torch's Event.from_ipc_handle objects
+    crashed in wait() with torch 2.11).  Owner: create(); others: open(handle). """
+
+    def __init__(self, lib_module, handle=None):
+        import ctypes
+        self._lib = lib_module
+        self.ptr = ctypes.c_void_p()
+        L = lib_module.lib()
+        if handle is None:
+            buf = ctypes.create_string_buffer(64)
+            lib_module.check(L.fb_ipc_event_create(ctypes.byref(self.ptr), buf))
+            self.handle = buf.raw
+        else:
+            self.handle = bytes(handle)
+            lib_module.check(L.fb_ipc_event_open(self.handle, ctypes.byref(self.ptr)))
+
+    def record(self, stream):
+        self._lib.check(self._lib.lib().fb_event_record(self.ptr, stream.cuda_stream))
+
+    def wait(self, stream):
+        """ work submitted to `stream` from now on waits for the most recent record (as of this call) """
+        self._lib.check(self._lib.lib().fb_stream_wait_event(stream.cuda_stream, self.ptr))
+
+
 class BarnesSlab3D:
     """
     3D optimized-convolution Barnes interpolation of ONE large volume split into z-slabs, one per
@@ -128,7 +153,7 @@ class BarnesSlab3D:
     """
 
     def __init__(self, sigma, x0, step, size, nsamples, method='optimized_convolution', num_iter=4, max_dist=3.5,
-                 group=None, device=None, want_float64=False, nslabs=None, slab=None, reserve_sms=0):
+                 group=None, device=None, want_float64=False, nslabs=None, slab=None, reserve_sms=0, exchange='nccl'):
         import torch
         import torch.distributed as dist
         from . import _lib
@@ -207,6 +232,109 @@ class BarnesSlab3D:
         # planes of mine that other ranks need: [z0, z0 + lo_need) and [z1 - hi_need, z1)
         self.lo_need = min(self.zc, self.halo) if self.rank > 0 else 0
         self.hi_need = min(self.zc, self.halo) if self.rank < self.world - 1 else 0
+        # transport of the halo planes: 'nccl' (send / recv kernels) or 'peer' (the ranks of one node map each other's
+        # buffers -- CUDA IPC -- and PULL the planes with device-to-device copies on the copy engines, which need no SM and
+        # therefore run beside the persistent sweep kernels; ordering by interprocess events)
+        self.exchange_mode = 'nccl'
+        if self.use_dist and exchange == 'peer':
+            self._setup_peer_exchange()
+
+    # -- peer-mapped exchange ------------------------------------------------------------------------
+    def _setup_peer_exchange(self):
+        """ Collective over the group: every rank publishes an IPC handle of its plane buffers and two interprocess
+        events, opens those of the ranks it pulls from, and all agree on whether the mapping worked everywhere. """
+        torch, dist = self.torch, self.dist
+        from torch.multiprocessing.reductions import reduce_tensor
+        ok = 1
+        try:
+            with torch.cuda.device(self.device):
+                self.ev_down = _IpcEvent(self._lib)      # my lowest planes are swept
+                self.ev_up = _IpcEvent(self._lib)        # my highest planes are swept
+                self.ev_pulled = _IpcEvent(self._lib)    # I have read my peers' planes
+                for e in (self.ev_down, self.ev_up, self.ev_pulled):
+                    e.record(torch.cuda.current_stream())
+                mine = {'rank': self.rank, 'device': self.device.index, 'ext0': self.ext0,
+                        'planes': [reduce_tensor(b) for b in self.planes],
+                        'events': [e.handle for e in (self.ev_down, self.ev_up, self.ev_pulled)]}
+        except Exception as e:                           # no IPC in this environment
+            mine, ok = {'rank': self.rank, 'error': repr(e)}, 0
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, mine, group=self.group)
+        self.peers = {}
+        if ok and all('error' not in m for m in everyone):
+            try:
+                need = {q for q, send, recv in self.transfers()}
+                for q in sorted(need):
+                    m = everyone[q]
+                    planes = [fn(*args) for fn, args in m['planes']]
+                    with torch.cuda.device(self.device):
+                        evs = [_IpcEvent(self._lib, h) for h in m['events']]
+                    self.peers[q] = {'ext0': m['ext0'], 'planes': planes, 'down': evs[0], 'up': evs[1], 'pulled': evs[2]}
+            except Exception:
+                ok = 0
+        else:
+            ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=self.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if int(flag.item()) == 1:
+            # host-side rendezvous (the order of event records and waits across processes is an order of host calls)
+            self.host_group = dist.new_group(backend='gloo')
+            self.exchange_mode = 'peer'
+            self.calls = 0
+        else:
+            self.peers = {}
+
+    def _host_barrier(self):
+        self.dist.barrier(group=self.host_group)
+
+    def _pull(self, direction):
+        """ copies, on the current stream, the planes that travel in `direction` from the ranks that own them into my
+        halo: 'down' = the lowest planes of the ranks above me, 'up' = the highest planes of the ranks below me """
+        torch = self.torch
+        cur = torch.cuda.current_stream()
+        for q, send, recv in self.transfers():
+            if not recv:
+                continue
+            d = 'up' if q < self.rank else 'down'
+            if d != direction:
+                continue
+            peer = self.peers[q]
+            peer[d].wait(cur)                            # the owner has swept those planes (its record precedes the host barrier)
+            for dst, src in zip(self.planes, peer['planes']):
+                dst[recv[0] - self.ext0:recv[1] - self.ext0].copy_(src[recv[0] - peer['ext0']:recv[1] - peer['ext0']],
+                                                                   non_blocking=True)
+
+    def _call_peer(self, pts, val):
+        torch = self.torch
+        with torch.cuda.device(self.device):
+            main, comm = torch.cuda.current_stream(), self.comm_stream
+            # the ranks that pull from me must have finished reading the planes of the previous call before I overwrite them
+            self._host_barrier()
+            for q, send, recv in self.transfers():
+                if send:
+                    self.peers[q]['pulled'].wait(main)
+            self.inject(pts, val)
+            lo, hi = self.lo_need, self.hi_need
+            if lo + hi >= self.zc:
+                self.sweeps(0, lo)
+                self.ev_down.record(main)
+                self.sweeps(lo, self.zc - lo)
+                self.ev_up.record(main)
+            else:
+                self.sweeps(0, lo)
+                self.ev_down.record(main)
+                self.sweeps(self.zc - hi, hi)
+                self.ev_up.record(main)
+            self._host_barrier()                         # every rank has issued its records of this call
+            comm.wait_stream(main)                       # (also behind the z sweep of the previous call, which read the halo)
+            with torch.cuda.stream(comm):
+                self._pull('down')
+                self._pull('up')
+                self.ev_pulled.record(comm)
+            if lo + hi < self.zc:
+                self.sweeps(lo, self.zc - lo - hi)       # the interior, while the copy engines move the halos
+            main.wait_stream(comm)
+        return self.phase2()
 
     # -- who sends what to whom --------------------------------------------------------------------
     def transfers(self):
@@ -290,6 +418,8 @@ class BarnesSlab3D:
         if not self.use_dist:
             self.phase1(pts, val)
             return self.phase2()
+        if self.exchange_mode == 'peer':
+            return self._call_peer(pts, val)
         torch = self.torch
         with torch.cuda.device(self.device):
             main = torch.cuda.current_stream()

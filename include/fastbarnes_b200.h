@@ -154,6 +154,16 @@ int fb_slab_result_offsets(const fb_problem *prob, int64_t nsamples, int64_t z_c
 int fb_slab_phase2_inplace_dev(const fb_problem *prob, int64_t z_begin, int64_t z_count, int64_t halo_lo, int64_t halo_hi,
                                int64_t nsamples, int want_out64, void *d_workspace, int64_t workspace_bytes, void *stream);
 
+/* Interprocess events for the peer-mapped halo exchange (one process per GPU on one node): an event created here can be
+ * opened in another process through its 64-byte handle; fb_event_record / fb_stream_wait_event are cudaEventRecord /
+ * cudaStreamWaitEvent on the given streams (0 = the default stream).  The order of a record and the wait that is meant to see
+ * it is the order of the two host calls: synchronise the processes between them. */
+int fb_ipc_event_create(void **event, void *handle64);
+int fb_ipc_event_open(const void *handle64, void **event);
+int fb_event_record(void *event, void *stream);
+int fb_stream_wait_event(void *stream, void *event);
+int fb_event_destroy(void *event);
+
 /* ---- stages (private-but-tested functions of the reference) -------------------------------- */
 /* interpolation.py:485-533 _accumulate_tail_array (alpha) / :729-772 _accumulate_array
  * (alpha = 0) applied in place to n_outer*n_inner independent lines of length len stored as

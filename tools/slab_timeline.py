@@ -22,7 +22,8 @@ rng = np.random.default_rng(1235)
 pts = rng.uniform(0, 1, (N, 3)) * [W - 1, H - 1, D - 1]
 val = rng.normal(0, 1, N)
 dp = torch.from_numpy(pts).to(dev); dv = torch.from_numpy(val).to(dev)
-slab = fd.BarnesSlab3D(sigma, [0.0] * 3, 1.0, (W, H, D), N, num_iter=4, reserve_sms=reserve)
+mode = sys.argv[2] if len(sys.argv) > 2 else 'nccl'
+slab = fd.BarnesSlab3D(sigma, [0.0] * 3, 1.0, (W, H, D), N, num_iter=4, reserve_sms=reserve, exchange=mode)
 L = _lib.lib()
 for _ in range(3):
     slab(dp, dv)
@@ -33,6 +34,38 @@ def ev():
 
 main, comm = torch.cuda.current_stream(), slab.comm_stream
 marks = []
+if slab.exchange_mode == 'peer':
+    # the peer-mapped exchange, step by step as BarnesSlab3D._call_peer does it
+    import time
+    t0 = ev(); h0 = time.perf_counter()
+    slab._host_barrier()
+    for q, send, recv in slab.transfers():
+        if send:
+            slab.peers[q]['pulled'].wait(main)
+    slab.inject(dp, dv); marks.append(('inject done', ev()))
+    lo, hi = slab.lo_need, slab.hi_need
+    slab.sweeps(0, lo); slab.ev_down.record(main); marks.append(('low boundary swept', ev()))
+    slab.sweeps(slab.zc - hi, hi); slab.ev_up.record(main); marks.append(('high boundary swept', ev()))
+    h1 = time.perf_counter()
+    slab._host_barrier()
+    h2 = time.perf_counter()
+    comm.wait_stream(main)
+    with torch.cuda.stream(comm):
+        marks.append(('pulls start', ev())); slab._pull('down'); marks.append(('down pulled', ev()))
+        slab._pull('up'); marks.append(('up pulled', ev())); slab.ev_pulled.record(comm)
+    slab.sweeps(lo, slab.zc - lo - hi); marks.append(('interior swept', ev()))
+    main.wait_stream(comm)
+    slab.phase2(); marks.append(('z sweep done', ev()))
+    torch.cuda.synchronize()
+    line = {'rank': rank, 'mode': 'peer', 'host_ms_enqueue_until_barrier': round((h1 - h0) * 1e3, 3), 'host_ms_barrier': round((h2 - h1) * 1e3, 3),
+            'ms': {k: round(t0.elapsed_time(e), 3) for k, e in marks}}
+    out = [None] * world
+    dist.all_gather_object(out, line)
+    if rank == 0:
+        for o in out:
+            print(json.dumps(o))
+    dist.barrier(); dist.destroy_process_group()
+    sys.exit(0)
 t0 = ev()
 slab.inject(dp, dv); marks.append(('inject done', ev()))
 lo, hi = slab.lo_need, slab.hi_need
