@@ -598,7 +598,7 @@ struct Pair { double *v, *w; };
 // wide kernels degrade to one launch per pass).  Launches with f >= 2 that keep the layout run in
 // place; single-pass launches and the transposing launch write to `spare`, after which the roles
 // of the two pairs swap.  On return `cur` holds the result (modes 0 and 1).
-// largest number of passes one launch can fuse / launches of a sweep / does its (single) launch run the hybrid kernel
+// largest number of passes one launch of the first-generation kernel can fuse
 inline int sweep_fmax(int mode, int D)
 {
     int fmax = 1;
@@ -898,10 +898,7 @@ int run_inject(const fb_problem *pr, const Derived &d, long long nsamples, const
     return FB_OK;
 }
 
-// The fp64 injection writes interleaved (value, weight) nodes when the x sweep that consumes them is the
-// hybrid kernel in a single launch (2D / 3D whole-grid path only; the z-slab path keeps planes).
-// The q path (fb_sweepq.cuh) runs every axis of a 2D / 3D fp64 grid on interleaved nodes; it needs a kernel
-// of at least 8 elements (D = 2T+2 >= 8) and on-chip rings on every axis.
+// The fp64 injection writes interleaved (value, weight) nodes when the sweeps that consume them run on nodes (use_nodes).
 // Per axis the grids of interleaved nodes are swept by the q kernels (fb_sweepq.cuh: every axis needs a kernel of at least 8
 // elements, D = 2T+2 >= 8, and on-chip rings) or, when the axis offers the q kernels too few units of work to fill the GPU,
 // by the pass-parallel kernels (fb_sweepp.cuh: any kernel whose rings fit in shared memory).

@@ -7,7 +7,7 @@
 // intrinsics, zero extension instead of the five loop phases) is the one of fb_sweep_chunk in
 // fb_kernels.cuh, so results are bit-identical to the reference and to the first-generation kernels.
 //
-// What is different from fb_sweeph_kernel (two warps per 16 lines, lock step, register-staged loads):
+// What is different from round 1's tensor-memory kernel (two warps per 16 lines in lock step, register-staged loads; removed):
 //   * Grids are arrays of interleaved (value, weight) fp64 nodes in every stage.  Lane l of a warp owns
 //     line l >> 1, field l & 1: a grid row of 16 lines is ONE contiguous 256-byte segment.
 //   * Input rows are fetched by TMA (`cp.async.bulk.tensor.3d...mbarrier::complete_tx::bytes`, SASS UTMALDG)
