@@ -919,8 +919,10 @@ int axis_path(const fb_problem *pr, const Derived &d, int m)
     const bool q_ok = g_sweepq.load() != 0 && sweepq_plan(pr->num_iter, axis_mode(pr, m), 2 * d.ax[m].T + 2).ok;
     const int pm = g_sweepp.load();
     const bool p_ok = pm != 0 && sweepp_plan(pr->num_iter, d.ax[m].T).ok;
-    if (p_ok && (pm >= 2 || !q_ok)) return FB_AXIS_P;
+    if (p_ok && pm >= 2) return FB_AXIS_P;
     // measured on the bench grid (2400 x 1200, T = 27, n = 4): the pass-parallel kernel wins up to 150 q units, ties at 225
+    // (large batches of kernels the q path does not cover -- fewer than 8 elements -- stay with the first-generation
+    // kernel, whose throughput is higher than the pass-parallel kernel's)
     if (p_ok && 2 * axis_q_items(pr, d, m) <= 3LL * sm_count_current()) return FB_AXIS_P;
     return q_ok ? FB_AXIS_Q : FB_AXIS_NONE;
 }
