@@ -61,6 +61,7 @@ struct FbSweepQ {
     int off_ring;                // byte offset of the rings inside that block (stages start at 128)
     // fb_sweepqs_kernel (rows from the binned samples, fb_sparse.cuh)
     int ncw;                     // pass warps per CTA (the producer warps follow them)
+    unsigned zero;               // always 0 (a value the compiler cannot fold: orders the early TMA request behind the loads)
     int nb;                      // buckets (chunks of 8 rows) per line group
     const unsigned int *bin_start;   // [n_outer * n_groups * nb + 1] first entry of every bucket
     int prod_bytes;                  // bytes of a pass warp's share of the producer area (mbarriers, bucket table, prefetch slots)
@@ -371,7 +372,11 @@ fb_sweepq_kernel(const FbSweepQ p, const __grid_constant__ CUtensorMap tm_in, co
     constexpr int U = FBQ_U;
     constexpr int NR = NPASS - 1;
     constexpr int NT = NR - NS;
+#ifdef FBQ_NO_EARLY
+    constexpr bool EARLY_ISSUE = false;
+#else
     constexpr bool EARLY_ISSUE = MODE != 2;
+#endif
     static_assert(NS >= 0 && NT >= 0, "ring split");
     extern __shared__ __align__(1024) unsigned char fbq_smem[];
     __shared__ unsigned s_tmem_base;
@@ -526,10 +531,15 @@ fb_sweepq_kernel(const FbSweepQ p, const __grid_constant__ CUtensorMap tm_in, co
             if constexpr (EARLY_ISSUE) {
                 // the staging slot is free as soon as every lane holds its rows in registers: request the chunk nst chunks
                 // ahead now, one chunk time earlier than at the end of the iteration (the memory-bound sweeps gain 4.5 %,
-                // the finalising sweep loses 2.7 % and keeps the late request).  `dep` is zero, but only known once the
-                // last loads of all lanes have returned.
-                unsigned dep = (unsigned)__popc(__double2hiint(bn[U - 1]) ^ __double2hiint(bo[U - 1])) >> 6;
-                dep = __reduce_or_sync(0xffffffffu, dep);
+                // the finalising sweep loses 2.7 % and keeps the late request).  `dep` is zero -- p.zero is a launch
+                // parameter that is always 0, which the compiler cannot know -- but only known once EVERY load of every lane
+                // has returned: the request is data dependent on all of them.  (A first version derived the zero from the
+                // last two loads alone, with arithmetic the assembler could fold: the request then overtook loads still
+                // in flight, and small 3D volumes came out wrong in a third of the runs -- found by tools/fuzz_parity.py.)
+                unsigned acc = 0u;
+#pragma unroll
+                for (int j = 0; j < U; ++j) acc ^= (unsigned)__double2hiint(bn[j]) ^ (unsigned)__double2hiint(bo[j]);
+                const unsigned dep = __reduce_or_sync(0xffffffffu, acc & p.zero);
                 issue(t + nst * U, slot, (int)(c + nst < nchunks) + (int)dep);
             }
             const unsigned sr = ring_s + (unsigned)rslot * 256u, sw = ring_s + (unsigned)wslot * 256u;

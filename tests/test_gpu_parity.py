@@ -1017,6 +1017,64 @@ def test_sweepq_wide_kernels_vs_oracle(fb, orc, T):
         _q_option(1, small_batch=1)
 
 
+@pytest.mark.parametrize('size,ratio,n,nf,N', [
+    ((88, 83, 58), (7.3, 7.1, 4.6), 2, 5, 2096),        # T = (7, 7, 4): in-place y sweep of a small volume, five fields
+    ((72, 53, 77), (2.9, 7.6, 13.2), 1, 5, 239),        # one pass: the y sweep writes into the injection buffer
+])
+def test_small_volumes_many_times(fb, orc, size, ratio, n, nf, N):
+    """ Regression (found by tools/fuzz_parity.py): the transposing / in-place q sweeps request their next staging chunk as
+    soon as the current one is in registers.  A first version of that request was not ordered behind ALL the loads; the
+    TMA unit then overwrote rows still being read, and small 3D volumes differed from the reference in about a third of
+    the runs (never the 2D bench batch).  Twenty runs of two such volumes, every field bit for bit. """
+    rng = np.random.default_rng(670)
+    step = 0.25
+    sigma = [r * step for r in ratio]
+    pts = rng.uniform(-0.03, 1.03, (nf, N, 3)) * (np.asarray(size) - 1) * step
+    pts[:, :60] = pts[:, 60:120]
+    val = rng.normal(100.0, 20.0, (nf, N))
+    refs = [orc.barnes(pts[i], val[i], sigma, [0.0] * 3, step, size, num_iter=n, nthreads=8) for i in range(nf)]
+    try:
+        _q_option(1, small_batch=0)
+        for run in range(20):
+            out = fb.barnes_batched(pts, val, sigma, [0.0] * 3, step, size, num_iter=n)
+            for i in range(nf):
+                assert bits_equal(out[i], refs[i]), (run, i)
+    finally:
+        _q_option(1, small_batch=1)
+
+
+def test_random_configurations_against_oracle(fb, orc):
+    """ A fixed-seed slice of tools/fuzz_parity.py: random 2D / 3D grids, kernel widths, pass counts, sample and field counts
+    through the default kernel choice, the q kernels alone, the pass-parallel kernels and the first-generation kernel. """
+    rng = np.random.default_rng(20261018)
+    done = 0
+    try:
+        while done < 40:
+            dim = int(rng.choice([2, 2, 3]))
+            n = int(rng.integers(1, 7))
+            size = tuple(int(x) for x in (rng.integers(40, 300, 2) if dim == 2 else rng.integers(24, 80, 3)))
+            step = float(rng.choice([0.1, 0.25, 1.0]))
+            ratio = rng.uniform(1.2, 12.0, dim) if dim == 3 else rng.uniform(1.2, 30.0, dim)
+            sigma = [float(r * step) for r in ratio]
+            if any(2 * fb.get_half_kernel_size_opt(sigma[m], step, n) + 1 >= size[m] for m in range(dim)):
+                continue
+            nf = int(rng.choice([1, 2, 5]))
+            N = int(rng.integers(30, 2000))
+            pts = rng.uniform(-0.03, 1.03, (nf, N, dim)) * (np.asarray(size) - 1) * step
+            k = min(N // 3, 80)
+            pts[:, :k] = pts[:, k:2 * k]
+            val = rng.normal(rng.uniform(-50, 500), rng.uniform(0.1, 30), (nf, N))
+            refs = [orc.barnes(pts[i], val[i], sigma, [0.0] * dim, step, size, num_iter=n, nthreads=8) for i in range(nf)]
+            for q, sb in ((1, 1), (1, 0), (1, 2), (0, 0)):
+                _q_option(q, small_batch=sb)
+                out = fb.barnes_batched(pts, val, sigma, [0.0] * dim, step, size, num_iter=n)
+                for i in range(nf):
+                    assert bits_equal(out[i], refs[i]), (done, dim, size, n, nf, N, (q, sb), i)
+            done += 1
+    finally:
+        _q_option(1, small_batch=1)
+
+
 def test_spare_buffers_with_very_wide_kernels(fb, orc):
     """ Kernels so wide that their rings do not fit on chip: the grid takes the first-generation path, where a launch
     covers one pass (2D) or the y sweep of a volume is split into several launches that are NOT in place -- the later
