@@ -558,7 +558,17 @@ fb_sweepq_kernel(const FbSweepQ p, const __grid_constant__ CUtensorMap tm_in, co
             // ---- the staging slot is free: request the chunk nst chunks ahead
             if constexpr (!EARLY_ISSUE) {
                 __syncwarp();
-                issue(t + nst * U, slot, c + nst < nchunks);
+                if constexpr (NPASS == 1) {
+                    // with rings, the ring stores above carry the values of every staged row and cannot issue before the
+                    // loads have returned; a single pass has no ring, so the request is tied to the loads explicitly
+                    unsigned acc = 0u;
+#pragma unroll
+                    for (int j = 0; j < U; ++j) acc ^= (unsigned)__double2hiint(bn[j]) ^ (unsigned)__double2hiint(bo[j]);
+                    const unsigned dep = __reduce_or_sync(0xffffffffu, acc & p.zero);
+                    issue(t + nst * U, slot, (int)(c + nst < nchunks) + (int)dep);
+                } else {
+                    issue(t + nst * U, slot, c + nst < nchunks);
+                }
             }
             if constexpr (NT > 0) fb_tmem_wait_st();
 #pragma unroll
