@@ -35,6 +35,7 @@ std::atomic<int> g_inject_lists{1};
 // second-generation sweep kernels (fb_sweepq.cuh): 0 off, non-zero (default) on for 2D / 3D fp64 grids they cover
 std::atomic<int> g_sweepq{1};
 std::atomic<int> g_q_reserve{0};    // SMs the q kernels leave free (z-slab runs: room for the exchange kernels)
+std::atomic<int> g_q_deep{1};       // transposing / in-place q sweeps: a fourth staging slot, with 7 warps where 8 do not fit
 std::atomic<int> g_q_nst{3};        // staging slots (chunks of rows in flight) per warp
 std::atomic<int> g_q_pf{0};         // extra chunks of lead of the L2 prefetch (0: none)
 std::atomic<int> g_sweepp{1};       // small batches: pass-parallel sweeps (fb_sweepp.cuh): 0 off, 1 when the batch is small, 2 always
@@ -166,6 +167,7 @@ size_t sweep_smem_bytes(int npass, int mode, int D)
 struct SweepQPlan {
     bool ok;
     int warps, ns, nst, R, RP, cols_per_warp, smem_per_warp, off_ring;
+    int launch_warps;            // warps a CTA is launched with (<= warps: the tensor-memory layout is that of `warps`)
 };
 constexpr size_t kQSmemLimit = 227 * 1024 - 1024;        // opt-in limit per CTA minus the kernel's static shared memory (1 KB with the alignment)
 
@@ -193,12 +195,25 @@ SweepQPlan sweepq_plan(int npass, int mode, int D, int header = 128, int extra_p
         if (nt > nr) nt = nr;
         const int ns = nr - nt;
         if (ns > 1) continue;
-        for (int nst = nst_want; nst >= 2; --nst) {
+        // Candidates (staging slots, warps per CTA): the finalising sweep and the sparse-fed sweep take the configured depth
+        // with all warps.  The transposing / in-place sweeps are memory bound and gain more from a fourth staging slot than
+        // they lose with one warp less (T = 27: 8 warps x 3 slots 1.138 ms, 7 x 3: 1.095, 7 x 4: 1.078, 6 x 5: 1.105), so
+        // they try 8 x 4, 7 x 4, then the configured depth downwards.
+        const int cap = nst_force > 0 ? warps : (mode == 2 ? g_q_cap_fin.load() : g_q_cap_xy.load());
+        const int wmax = (cap >= 1 && cap < warps) ? cap : warps;
+        int cand[16][2], nc = 0;
+        if (mode != 2 && nst_force == 0 && warps == 8 && nst_want < 4 && g_q_deep.load() != 0) {
+            cand[nc][0] = 4; cand[nc++][1] = wmax;
+            if (wmax == 8) { cand[nc][0] = 4; cand[nc++][1] = 7; }
+        }
+        for (int nst = nst_want; nst >= 2 && nc < 16; --nst) { cand[nc][0] = nst; cand[nc++][1] = wmax; }
+        for (int i = 0; i < nc; ++i) {
+            const int nst = cand[i][0], wfit = cand[i][1];
             const size_t off_ring = (size_t)header + (size_t)nst * FBQ_STAGE_BYTES;
             const size_t per = off_ring + (size_t)ns * q.RP * 256;
-            if (sweepq_smem_bytes(mode, warps, (int)per) + (size_t)warps * extra_per_warp > kQSmemLimit) continue;
+            if (sweepq_smem_bytes(mode, wfit, (int)per) + (size_t)wfit * extra_per_warp > kQSmemLimit) continue;
             q.ok = true;
-            q.warps = warps; q.ns = ns; q.nst = nst; q.cols_per_warp = cols;
+            q.warps = warps; q.launch_warps = wfit; q.ns = ns; q.nst = nst; q.cols_per_warp = cols;
             q.smem_per_warp = (int)per; q.off_ring = (int)off_ring;
             return q;
         }
@@ -279,9 +294,7 @@ int launch_sweepq_t(FbSweepQ p, const SweepQPlan &q, cudaStream_t st)
     if (rc != FB_OK) return rc;
     const int sms = sm_count(dev);
     // few items: spread them over the SMs with fewer warps per CTA
-    int warps = q.warps;
-    const int cap = MODE == 2 ? g_q_cap_fin.load() : g_q_cap_xy.load();
-    if (cap >= 1 && warps > cap) warps = cap;
+    int warps = q.launch_warps > 0 ? q.launch_warps : q.warps;
     if (nitems < (long long)sms * warps) {
         warps = (int)((nitems + sms - 1) / sms);
         if (warps < 1) warps = 1;
@@ -2425,6 +2438,7 @@ FB_EXPORT int fb_set_option(const char *name, int value)
     if (!strcmp(name, "host_chunk_fields")) { g_host_chunk_fields.store(value); return FB_OK; }
     if (!strcmp(name, "sweepq")) { g_sweepq.store(value); return FB_OK; }
     if (!strcmp(name, "sweepq_stages")) { g_q_nst.store(value); return FB_OK; }
+    if (!strcmp(name, "sweepq_deep_staging")) { g_q_deep.store(value); return FB_OK; }
     if (!strcmp(name, "sweepq_prefetch")) { g_q_pf.store(value); return FB_OK; }
     if (!strcmp(name, "sweepq_warps")) { g_q_warps.store(value); return FB_OK; }
     if (!strcmp(name, "sweepq_cap_warps_xy")) { g_q_cap_xy.store(value); return FB_OK; }

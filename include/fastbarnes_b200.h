@@ -243,6 +243,8 @@ int fb_barnes_s2_map_host(int64_t nsamples, const double *pts, const double *val
  *       staging, rings in tensor + shared memory) wherever 2T+2 >= 8 and the rings fit on chip; 0: first-generation kernel
  *   "sweepq_stages" (default 3), "sweepq_prefetch" (default 0), "sweepq_warps" (default 8): staging slots per warp, extra
  *       L2 prefetch lead in chunks, warps per CTA of the q kernels
+ *   "sweepq_deep_staging" (default 1): the transposing / in-place q sweeps take a fourth staging slot, with 7 warps per CTA
+ *       where 8 do not fit;  "sweepq_cap_warps_xy" / "sweepq_cap_warps_final" (default 8): most warps per CTA
  *   "sweepq_reserve_sms" (default 0): SMs the persistent q kernels leave free (room for kernels of other streams)
  *   "sweepp" (default 1): pass-parallel kernels for small batches: 0 off, 1 per axis when the q kernel would have at most
  *       1.5 x SMs units of work (or cannot run), 2 always
