@@ -5,7 +5,7 @@
 # racecheck tracks, the mbarrier waits are what orders it.
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-CASES='test_barnes_golden or test_line_kernel_golden or test_sweepq_wide_kernels_vs_oracle or test_sweepq_vs_first_generation or test_1d_exact_default_and_segmented_option or test_z_slab_decomposition_single_gpu or test_injection_lists_vs_segments'
+CASES='test_small_volumes_many_times or test_barnes_golden or test_line_kernel_golden or test_sweepq_wide_kernels_vs_oracle or test_sweepq_vs_first_generation or test_1d_exact_default_and_segmented_option or test_z_slab_decomposition_single_gpu or test_injection_lists_vs_segments'
 for tool in ${TOOLS:-memcheck racecheck synccheck}; do
   out=gpurun_out/sanitizer_$tool.txt
   {
