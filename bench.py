@@ -554,13 +554,16 @@ def run_gpu(args, rank, local_rank, world):
     probe_reps = 4
     probe_dst = out_pin[:SUB]
     probe_dst.copy_(d_out, non_blocking=True)
-    barrier()
-    p0.record()
-    for _ in range(probe_reps):
-        probe_dst.copy_(d_out, non_blocking=True)
-    p1.record()
-    barrier()
-    d2h_ms = p0.elapsed_time(p1) / probe_reps
+    d2h_ms = None
+    for _ in range(3):                               # the best of three rounds: a ceiling, not an average
+        barrier()
+        p0.record()
+        for _ in range(probe_reps):
+            probe_dst.copy_(d_out, non_blocking=True)
+        p1.record()
+        barrier()
+        ms_round = p0.elapsed_time(p1) / probe_reps
+        d2h_ms = ms_round if d2h_ms is None or ms_round < d2h_ms else d2h_ms
 
     # ---- reduce over ranks (max time) ------------------------------------------------------------------
     t = torch.tensor([ms_total, e2e_s * 1e3, fp32[0] if fp32 else 0.0, d2h_ms], dtype=torch.float64, device=dev)
